@@ -1,0 +1,329 @@
+// api.cu -- C ABI of libqcsim_b200.so (see include/qcsim_b200.h for the contract and the
+// reference members each entry point replaces).  Host logic only: argument checks with the
+// reference's error conventions, gate classification, kernel launches on the handle's stream.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/qcsim_b200.h"
+#include "engine.h"
+
+using namespace qcsim;
+
+namespace qcsim {
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+}  // namespace qcsim
+
+#define API_GUARD(h)                                                            \
+  if (!(h)) return fail(QCSIM_ERR_BAD_ARG, "null register handle");             \
+  {                                                                             \
+    cudaError_t e__ = cudaSetDevice((h)->device);                               \
+    if (e__ != cudaSuccess) return fail(QCSIM_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e__)); \
+  }
+
+extern "C" {
+
+const char* qcsim_last_error(void) { return g_last_error.c_str(); }
+int qcsim_abi_version(void) { return QCSIM_ABI_VERSION; }
+
+int qcsim_device_count(int* count) {
+  if (!count) return fail(QCSIM_ERR_BAD_ARG, "null count");
+  cudaError_t e = cudaGetDeviceCount(count);
+  if (e != cudaSuccess) {
+    *count = 0;
+    return fail(QCSIM_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+  }
+  return QCSIM_OK;
+}
+
+int qcsim_sv_create(qcsim_sv** out, int n_qubits, int device) {
+  return engine_create(out, n_qubits, device, 0, 1, nullptr);
+}
+
+int qcsim_nccl_unique_id(void* out_128_bytes) { return engine_nccl_unique_id(out_128_bytes); }
+
+int qcsim_sv_create_sharded(qcsim_sv** out, int n_qubits, int device, int rank, int world, const void* nccl_id) {
+  return engine_create(out, n_qubits, device, rank, world, nccl_id);
+}
+
+int qcsim_sv_destroy(qcsim_sv* h) {
+  if (!h) return QCSIM_OK;
+  cudaSetDevice(h->device);
+  return engine_destroy(h);
+}
+
+int qcsim_sv_clone(const qcsim_sv* src, qcsim_sv** out) {
+  if (!src || !out) return fail(QCSIM_ERR_BAD_ARG, "null argument");
+  return engine_clone(src, out);
+}
+
+int qcsim_sv_sync(qcsim_sv* h) {
+  API_GUARD(h);
+  QCSIM_TRY(engine_flush(h));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return QCSIM_OK;
+}
+
+int qcsim_sv_n_qubits(const qcsim_sv* h, int* n_qubits, int* n_local_qubits) {
+  if (!h) return fail(QCSIM_ERR_BAD_ARG, "null register handle");
+  if (n_qubits) *n_qubits = h->n;
+  if (n_local_qubits) *n_local_qubits = h->n_local;
+  return QCSIM_OK;
+}
+
+int qcsim_sv_device_ptr(qcsim_sv* h, void** dptr, void** cuda_stream) {
+  API_GUARD(h);
+  QCSIM_TRY(engine_flush(h));
+  QCSIM_TRY(engine_canonicalize(h));
+  if (dptr) *dptr = h->psi;
+  if (cuda_stream) *cuda_stream = (void*)h->stream;
+  return QCSIM_OK;
+}
+
+/* ---- state setters / getters ---------------------------------------------------------------- */
+
+int qcsim_sv_set_basis_state(qcsim_sv* h, uint64_t state) {
+  API_GUARD(h);
+  if (state >= h->dim) return fail(QCSIM_ERR_BAD_STATE, "basis state out of range");
+  engine_drop_queue(h);
+  return engine_set_basis_state(h, state);
+}
+
+int qcsim_sv_fill(qcsim_sv* h, double re, double im) {
+  API_GUARD(h);
+  engine_drop_queue(h);
+  return engine_fill(h, re, im);
+}
+
+int qcsim_sv_set_amplitude(qcsim_sv* h, uint64_t state, double re, double im) {
+  API_GUARD(h);
+  if (state >= h->dim) return fail(QCSIM_ERR_BAD_STATE, "basis state out of range");
+  QCSIM_TRY(engine_flush(h));
+  return engine_set_amplitude(h, state, re, im);
+}
+
+int qcsim_sv_get_amplitude(qcsim_sv* h, uint64_t state, double* re_im) {
+  API_GUARD(h);
+  if (!re_im) return fail(QCSIM_ERR_BAD_ARG, "null output");
+  if (state >= h->dim) {
+    re_im[0] = re_im[1] = 0;
+    return fail(QCSIM_ERR_BAD_STATE, "basis state out of range");
+  }
+  QCSIM_TRY(engine_flush(h));
+  return engine_get_amplitude(h, state, re_im);
+}
+
+int qcsim_sv_upload(qcsim_sv* h, const double* host, uint64_t first, uint64_t count) {
+  API_GUARD(h);
+  if (!host && count) return fail(QCSIM_ERR_BAD_ARG, "null host buffer");
+  QCSIM_TRY(engine_flush(h));
+  return engine_transfer(h, const_cast<double*>(host), first, count, /*to_device=*/true);
+}
+
+int qcsim_sv_download(qcsim_sv* h, double* host, uint64_t first, uint64_t count) {
+  API_GUARD(h);
+  if (!host && count) return fail(QCSIM_ERR_BAD_ARG, "null host buffer");
+  QCSIM_TRY(engine_flush(h));
+  return engine_transfer(h, host, first, count, /*to_device=*/false);
+}
+
+int qcsim_sv_norm2(qcsim_sv* h, double* out) {
+  API_GUARD(h);
+  if (!out) return fail(QCSIM_ERR_BAD_ARG, "null output");
+  QCSIM_TRY(engine_flush(h));
+  return engine_masked_norm2(h, 0, 0, out);
+}
+
+int qcsim_sv_scale(qcsim_sv* h, double factor) {
+  API_GUARD(h);
+  QCSIM_TRY(engine_flush(h));
+  return engine_scale(h, factor);
+}
+
+int qcsim_sv_normalize(qcsim_sv* h) {
+  API_GUARD(h);
+  QCSIM_TRY(engine_flush(h));
+  double n2 = 0;
+  QCSIM_TRY(engine_masked_norm2(h, 0, 0, &n2));
+  const double norm = std::sqrt(n2);
+  if (norm < 1E-20) return QCSIM_OK;  // QubitRegister.h:127
+  return engine_scale(h, 1. / norm);
+}
+
+int qcsim_sv_save_state(qcsim_sv* h) {
+  API_GUARD(h);
+  QCSIM_TRY(engine_flush(h));
+  return engine_save(h);
+}
+
+int qcsim_sv_restore_state(qcsim_sv* h, int destructive) {
+  API_GUARD(h);
+  engine_drop_queue(h);
+  return engine_restore(h, destructive != 0);
+}
+
+int qcsim_sv_inner_product(qcsim_sv* a, qcsim_sv* b, double* re_im) {
+  API_GUARD(a);
+  if (!b || !re_im) return fail(QCSIM_ERR_BAD_ARG, "null argument");
+  QCSIM_TRY(engine_flush(a));
+  QCSIM_TRY(engine_flush(b));
+  return engine_inner_product(a, b, re_im);
+}
+
+/* ---- gates ------------------------------------------------------------------------------------ */
+
+static int check_qubits(const qcsim_sv* h, int nq, uint64_t q, uint64_t c1, uint64_t c2) {
+  // QubitRegister::CheckQubits, QubitRegister.h:677-690 (same order of tests, same messages)
+  const uint64_t n = (uint64_t)h->n;
+  if (nq < 1 || nq > 3) return fail(QCSIM_ERR_BAD_ARG, "gate must act on 1, 2 or 3 qubits");
+  if (n <= q) return fail(QCSIM_ERR_QUBIT_TOO_HIGH, "Qubit number is too high");
+  if (nq == 2) {
+    if (n <= c1) return fail(QCSIM_ERR_CTRL_TOO_HIGH, "Controlling qubit number is too high");
+    if (q == c1) return fail(QCSIM_ERR_SAME_QUBITS, "Qubit and controlling qubit are the same");
+  } else if (nq == 3) {
+    if (n <= c1 || n <= c2) return fail(QCSIM_ERR_CTRL_TOO_HIGH, "Controlling qubit number is too high");
+    if (q == c1 || q == c2 || c1 == c2) return fail(QCSIM_ERR_SAME_QUBITS, "Qubits must be different");
+  }
+  return QCSIM_OK;
+}
+
+int qcsim_sv_apply(qcsim_sv* h, int nq, const double* m, int flags, uint64_t q, uint64_t c1, uint64_t c2) {
+  API_GUARD(h);
+  if (!m) return fail(QCSIM_ERR_BAD_ARG, "null matrix");
+  QCSIM_TRY(check_qubits(h, nq, q, c1, c2));
+  h->stats.gates_applied++;
+  const Op op = classify(nq, m, flags, q, c1, c2);
+  if (h->fusion) return engine_enqueue(h, op);
+  return engine_apply_now(h, op);
+}
+
+int qcsim_sv_apply_batch(qcsim_sv* h, const qcsim_gate* gates, uint64_t count) {
+  API_GUARD(h);
+  if (!gates && count) return fail(QCSIM_ERR_BAD_ARG, "null gate list");
+  for (uint64_t i = 0; i < count; ++i) QCSIM_TRY(check_qubits(h, gates[i].nq, gates[i].q, gates[i].c1, gates[i].c2));
+  for (uint64_t i = 0; i < count; ++i) {
+    const qcsim_gate& g = gates[i];
+    h->stats.gates_applied++;
+    QCSIM_TRY(engine_enqueue(h, classify(g.nq, g.m, g.flags, g.q, g.c1, g.c2)));
+  }
+  if (!h->fusion) return engine_flush(h);
+  return QCSIM_OK;
+}
+
+int qcsim_sv_set_fusion(qcsim_sv* h, int enabled) {
+  API_GUARD(h);
+  if (!enabled) QCSIM_TRY(engine_flush(h));
+  h->fusion = enabled != 0;
+  return QCSIM_OK;
+}
+
+int qcsim_sv_qft(qcsim_sv* h, uint64_t sq, uint64_t eq, int do_swap, int inverse) {
+  API_GUARD(h);
+  return engine_qft(h, sq, eq, do_swap != 0, inverse != 0);
+}
+
+/* ---- measurement ---------------------------------------------------------------------------- */
+
+int qcsim_sv_measure_all(qcsim_sv* h, double prob, uint64_t* outcome) {
+  API_GUARD(h);
+  if (!outcome) return fail(QCSIM_ERR_BAD_ARG, "null output");
+  QCSIM_TRY(engine_flush(h));
+  uint64_t s = 0;
+  QCSIM_TRY(engine_pick_state(h, prob, h->dim - 1, &s));  // fallback: last state, QubitRegister.h:173
+  QCSIM_TRY(engine_set_basis_state(h, s));                // collapse, :192
+  *outcome = s;
+  return QCSIM_OK;
+}
+
+int qcsim_sv_measure_all_nocollapse(qcsim_sv* h, double prob, uint64_t* outcome) {
+  API_GUARD(h);
+  if (!outcome) return fail(QCSIM_ERR_BAD_ARG, "null output");
+  QCSIM_TRY(engine_flush(h));
+  return engine_pick_state(h, prob, 0, outcome);  // fallback 0, QubitRegister.h:623
+}
+
+static int measured_mask(const qcsim_sv* h, uint64_t first, uint64_t last, uint64_t* mask) {
+  if (first > last || last >= (uint64_t)h->n) return fail(QCSIM_ERR_BAD_ARG, "bad measured qubit range");
+  const uint64_t low = (1ULL << first) - 1ULL;
+  const uint64_t upto = (last + 1 >= 64) ? ~0ULL : ((1ULL << (last + 1)) - 1ULL);
+  *mask = upto - low;  // QubitRegisterCalculator.h:1128-1130
+  return QCSIM_OK;
+}
+
+int qcsim_sv_measure(qcsim_sv* h, uint64_t first, uint64_t last, double prob, uint64_t* outcome) {
+  API_GUARD(h);
+  if (!outcome) return fail(QCSIM_ERR_BAD_ARG, "null output");
+  uint64_t mask = 0;
+  QCSIM_TRY(measured_mask(h, first, last, &mask));
+  QCSIM_TRY(engine_flush(h));
+  uint64_t s = 0;
+  QCSIM_TRY(engine_pick_state(h, prob, 0, &s));  // fallback 0, QubitRegisterCalculator.h:954,1132
+  const uint64_t want = s & mask;
+  double acc = 0;
+  QCSIM_TRY(engine_masked_norm2(h, mask, want, &acc));
+  QCSIM_TRY(engine_collapse(h, mask, want, 1. / std::sqrt(acc)));
+  *outcome = want >> first;
+  return QCSIM_OK;
+}
+
+int qcsim_sv_measure_nocollapse(qcsim_sv* h, uint64_t first, uint64_t last, double prob, uint64_t* outcome) {
+  API_GUARD(h);
+  if (!outcome) return fail(QCSIM_ERR_BAD_ARG, "null output");
+  uint64_t mask = 0;
+  QCSIM_TRY(measured_mask(h, first, last, &mask));
+  QCSIM_TRY(engine_flush(h));
+  uint64_t s = 0;
+  QCSIM_TRY(engine_pick_state(h, prob, 0, &s));
+  *outcome = (s & mask) >> first;
+  return QCSIM_OK;
+}
+
+int qcsim_sv_qubit_probability(qcsim_sv* h, uint64_t q, double* p) {
+  API_GUARD(h);
+  if (!p) return fail(QCSIM_ERR_BAD_ARG, "null output");
+  if (q >= (uint64_t)h->n) return fail(QCSIM_ERR_QUBIT_TOO_HIGH, "Qubit number is too high");
+  QCSIM_TRY(engine_flush(h));
+  return engine_masked_norm2(h, 1ULL << q, 1ULL << q, p);
+}
+
+int qcsim_sv_sample(qcsim_sv* h, const double* probs, uint64_t count, uint64_t* outcomes) {
+  API_GUARD(h);
+  if ((!probs || !outcomes) && count) return fail(QCSIM_ERR_BAD_ARG, "null argument");
+  QCSIM_TRY(engine_flush(h));
+  return engine_sample(h, probs, count, outcomes);
+}
+
+int qcsim_sv_set_strict_measure(qcsim_sv* h, int enabled) {
+  if (!h) return fail(QCSIM_ERR_BAD_ARG, "null register handle");
+  h->strict_measure = enabled != 0;
+  return QCSIM_OK;
+}
+
+int qcsim_sv_get_stats(const qcsim_sv* h, qcsim_stats* out) {
+  if (!h || !out) return fail(QCSIM_ERR_BAD_ARG, "null argument");
+  *out = h->stats;
+  return QCSIM_OK;
+}
+
+int qcsim_sv_reset_stats(qcsim_sv* h) {
+  if (!h) return fail(QCSIM_ERR_BAD_ARG, "null register handle");
+  std::memset(&h->stats, 0, sizeof(h->stats));
+  return QCSIM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,20 @@
+// dist.h -- sharded registers: the state is split over `world` GPUs on its top log2(world)
+// qubits; one process per GPU.  See dist.cu.
+#pragma once
+
+#include "engine.h"
+
+namespace qcsim {
+
+int dist_init(qcsim_sv* h, const void* nccl_id);
+void dist_shutdown(qcsim_sv* h);
+int dist_unique_id(void* out128);
+void dist_reset_layout(qcsim_sv* h);
+int dist_buffers_changed(qcsim_sv* h);
+void dist_map_mask(qcsim_sv* h, uint64_t mask, uint64_t want, uint64_t* pmask, uint64_t* pwant);
+int dist_allreduce_host(qcsim_sv* h, double* vals, int count);
+int dist_apply(qcsim_sv* h, const Op& op);
+int dist_canonicalize(qcsim_sv* h);
+int dist_pick_state(qcsim_sv* h, double prob, uint64_t fallback, uint64_t* outcome);
+
+}  // namespace qcsim

@@ -1,0 +1,515 @@
+// engine.cu -- host side of the engine: owns the device buffers, lowers classified ops to
+// kernel launches on the handle's stream.  Single-GPU paths live here; sharding is in dist.cu.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "engine.h"
+#include "gate_kernels.cuh"
+#include "reduce_kernels.cuh"
+#include "dist.h"
+#include "fusion.h"
+
+namespace qcsim {
+
+constexpr int kMaxPartials = kNumSMs * 8;
+
+static inline int grid_for(uint64_t threads_needed) {
+  uint64_t b = (threads_needed + kThreads - 1) / kThreads;
+  if (b < 1) b = 1;
+  if (b > (uint64_t)kMaxPartials) b = kMaxPartials;
+  return (int)b;
+}
+
+static inline void count_pass(qcsim_sv* h, uint64_t amps_touched, int launches = 1) {
+  h->stats.kernel_launches += launches;
+  h->stats.state_passes += 1;
+  h->stats.bytes_moved += 32ULL * amps_touched;
+}
+
+static inline amp to_amp(const cplx& z) { return make_amp(z.real(), z.imag()); }
+
+// ---- lifecycle ---------------------------------------------------------------------------------
+
+int engine_create(qcsim_sv** out, int n_qubits, int device, int rank, int world, const void* nccl_id) {
+  if (!out) return fail(QCSIM_ERR_BAD_ARG, "null output handle");
+  *out = nullptr;
+  if (n_qubits < 1 || n_qubits > 48) return fail(QCSIM_ERR_BAD_ARG, "n_qubits must be in 1..48");
+  if (world < 1 || (world & (world - 1)) || rank < 0 || rank >= world)
+    return fail(QCSIM_ERR_BAD_ARG, "world must be a power of two and 0 <= rank < world");
+  int log2w = 0;
+  while ((1 << log2w) < world) ++log2w;
+  if (n_qubits - log2w < 1) return fail(QCSIM_ERR_BAD_ARG, "too few qubits for this many shards");
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0)
+    return fail(QCSIM_ERR_CUDA, "no CUDA device (%s); qcsim_b200 has no CPU fallback",
+                ce == cudaSuccess ? "device count is 0" : cudaGetErrorString(ce));
+  if (device < 0 || device >= ndev) return fail(QCSIM_ERR_BAD_ARG, "device %d out of range (%d devices)", device, ndev);
+  CUDA_TRY(cudaSetDevice(device));
+
+  qcsim_sv* h = new qcsim_sv();
+  h->n = n_qubits;
+  h->n_local = n_qubits - log2w;
+  h->dim = 1ULL << n_qubits;
+  h->dim_local = 1ULL << h->n_local;
+  h->device = device;
+  h->rank = rank;
+  h->world = world;
+  auto bail = [&](int rc) {
+    engine_destroy(h);
+    return rc;
+  };
+#define CREATE_TRY(expr)                                                                             \
+  do {                                                                                               \
+    const cudaError_t ce__ = (expr);                                                                 \
+    if (ce__ != cudaSuccess)                                                                         \
+      return bail(fail(ce__ == cudaErrorMemoryAllocation ? QCSIM_ERR_OOM : QCSIM_ERR_CUDA, "%s: %s", #expr, \
+                       cudaGetErrorString(ce__)));                                                   \
+  } while (0)
+  CREATE_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CREATE_TRY(cudaMalloc(&h->psi, h->dim_local * sizeof(amp)));
+  CREATE_TRY(cudaMalloc(&h->d_partials, 2 * kMaxPartials * sizeof(double)));
+  CREATE_TRY(cudaMalloc(&h->d_scalars, 64 * sizeof(double)));
+  h->n_chunks = (h->dim_local + kChunk - 1) / kChunk;
+  CREATE_TRY(cudaMalloc(&h->d_chunk_sums, h->n_chunks * sizeof(dd)));
+  CREATE_TRY(cudaMalloc(&h->d_scan, sizeof(ScanResult)));
+  CREATE_TRY(cudaMallocHost(&h->h_pinned, 4096));
+#undef CREATE_TRY
+  if (world > 1) {
+    const int rc = dist_init(h, nccl_id);
+    if (rc != QCSIM_OK) return bail(rc);
+  }
+  const int rc = engine_set_basis_state(h, 0);  // QubitRegister.h:36
+  if (rc != QCSIM_OK) return bail(rc);
+  *out = h;
+  return QCSIM_OK;
+}
+
+int engine_destroy(qcsim_sv* h) {
+  if (!h) return QCSIM_OK;
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->world > 1) dist_shutdown(h);
+  cudaFree(h->psi);
+  cudaFree(h->saved);
+  cudaFree(h->d_partials);
+  cudaFree(h->d_scalars);
+  cudaFree(h->d_chunk_sums);
+  cudaFree(h->d_scan);
+  if (h->h_pinned) cudaFreeHost(h->h_pinned);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return QCSIM_OK;
+}
+
+int engine_clone(const qcsim_sv* src, qcsim_sv** out) {
+  if (src->world > 1) return fail(QCSIM_ERR_UNSUPPORTED, "clone of a sharded register is not supported");
+  qcsim_sv* s = const_cast<qcsim_sv*>(src);
+  CUDA_TRY(cudaSetDevice(s->device));
+  QCSIM_TRY(engine_flush(s));
+  qcsim_sv* h = nullptr;
+  QCSIM_TRY(engine_create(&h, src->n, src->device, 0, 1, nullptr));
+  h->fusion = src->fusion;
+  h->strict_measure = src->strict_measure;
+  cudaError_t ce = cudaStreamSynchronize(s->stream);
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(h->psi, s->psi, s->dim_local * sizeof(amp), cudaMemcpyDeviceToDevice, h->stream);
+  if (ce == cudaSuccess && s->saved) {
+    ce = cudaMalloc(&h->saved, s->dim_local * sizeof(amp));
+    if (ce == cudaSuccess)
+      ce = cudaMemcpyAsync(h->saved, s->saved, s->dim_local * sizeof(amp), cudaMemcpyDeviceToDevice, h->stream);
+  }
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(h->stream);
+  if (ce != cudaSuccess) {
+    engine_destroy(h);
+    return fail(ce == cudaErrorMemoryAllocation ? QCSIM_ERR_OOM : QCSIM_ERR_CUDA, "clone: %s", cudaGetErrorString(ce));
+  }
+  *out = h;
+  return QCSIM_OK;
+}
+
+// ---- state setters / getters -------------------------------------------------------------------
+
+__global__ void k_set_amp(amp* psi, uint64_t idx, amp v) { psi[idx] = v; }
+
+int engine_fill(qcsim_sv* h, double re, double im) {
+  if (h->world > 1) dist_reset_layout(h);
+  if (re == 0.0 && im == 0.0) {
+    CUDA_TRY(cudaMemsetAsync(h->psi, 0, h->dim_local * sizeof(amp), h->stream));
+  } else {
+    k_fill<<<grid_for(h->dim_local), kThreads, 0, h->stream>>>(h->psi, h->dim_local, make_amp(re, im));
+    CUDA_TRY(cudaGetLastError());
+    h->stats.kernel_launches++;
+  }
+  return QCSIM_OK;
+}
+
+int engine_set_basis_state(qcsim_sv* h, uint64_t state) {
+  QCSIM_TRY(engine_fill(h, 0, 0));  // Clear(), QubitRegister.h:78
+  const uint64_t owner = state >> h->n_local;
+  if (owner == (uint64_t)h->rank) {
+    k_set_amp<<<1, 1, 0, h->stream>>>(h->psi, state & (h->dim_local - 1), make_amp(1, 0));
+    CUDA_TRY(cudaGetLastError());
+    h->stats.kernel_launches++;
+  }
+  return QCSIM_OK;
+}
+
+int engine_set_amplitude(qcsim_sv* h, uint64_t state, double re, double im) {
+  QCSIM_TRY(engine_canonicalize(h));
+  if ((state >> h->n_local) != (uint64_t)h->rank) return QCSIM_OK;  // other rank's element
+  k_set_amp<<<1, 1, 0, h->stream>>>(h->psi, state & (h->dim_local - 1), make_amp(re, im));
+  CUDA_TRY(cudaGetLastError());
+  h->stats.kernel_launches++;
+  return QCSIM_OK;
+}
+
+int engine_get_amplitude(qcsim_sv* h, uint64_t state, double* re_im) {
+  QCSIM_TRY(engine_canonicalize(h));
+  double* stage = (double*)h->h_pinned;
+  stage[0] = stage[1] = 0;
+  if ((state >> h->n_local) == (uint64_t)h->rank)
+    CUDA_TRY(cudaMemcpyAsync(stage, h->psi + (state & (h->dim_local - 1)), sizeof(amp), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (h->world > 1) QCSIM_TRY(dist_allreduce_host(h, stage, 2));
+  re_im[0] = stage[0];
+  re_im[1] = stage[1];
+  return QCSIM_OK;
+}
+
+int engine_transfer(qcsim_sv* h, double* host, uint64_t first, uint64_t count, bool to_device) {
+  QCSIM_TRY(engine_canonicalize(h));
+  const uint64_t base = (uint64_t)h->rank << h->n_local;
+  if (count == 0) return QCSIM_OK;
+  if (first < base || first + count > base + h->dim_local || first + count < first)
+    return fail(QCSIM_ERR_BAD_ARG, "range [%llu, +%llu) is outside this rank's slice", (unsigned long long)first,
+                (unsigned long long)count);
+  amp* d = h->psi + (first - base);
+  if (to_device)
+    CUDA_TRY(cudaMemcpyAsync(d, host, count * sizeof(amp), cudaMemcpyHostToDevice, h->stream));
+  else
+    CUDA_TRY(cudaMemcpyAsync(host, d, count * sizeof(amp), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return QCSIM_OK;
+}
+
+int engine_masked_norm2(qcsim_sv* h, uint64_t mask, uint64_t want, double* out) {
+  // logical (mask, want) -> physical bit positions of the current layout
+  uint64_t pmask = mask, pwant = want;
+  if (h->world > 1) dist_map_mask(h, mask, want, &pmask, &pwant);
+  const int g = grid_for(h->dim_local / 2);
+  const uint64_t base = (uint64_t)h->rank << h->n_local;
+  k_masked_norm2<<<g, kThreads, 0, h->stream>>>(h->psi, h->dim_local, base, pmask, pwant, h->d_partials);
+  k_final_sum<<<1, kThreads, 0, h->stream>>>(h->d_partials, g, 1, h->d_scalars);
+  CUDA_TRY(cudaGetLastError());
+  h->stats.kernel_launches += 2;
+  h->stats.state_passes += 1;
+  h->stats.bytes_moved += 16ULL * h->dim_local;
+  double* stage = (double*)h->h_pinned;
+  CUDA_TRY(cudaMemcpyAsync(stage, h->d_scalars, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (h->world > 1) QCSIM_TRY(dist_allreduce_host(h, stage, 1));
+  *out = stage[0];
+  return QCSIM_OK;
+}
+
+int engine_scale(qcsim_sv* h, double f) {
+  k_scale<<<grid_for(h->dim_local), kThreads, 0, h->stream>>>(h->psi, h->dim_local, f);
+  CUDA_TRY(cudaGetLastError());
+  count_pass(h, h->dim_local);
+  return QCSIM_OK;
+}
+
+int engine_collapse(qcsim_sv* h, uint64_t mask, uint64_t want, double f) {
+  uint64_t pmask = mask, pwant = want;
+  if (h->world > 1) dist_map_mask(h, mask, want, &pmask, &pwant);
+  const uint64_t base = (uint64_t)h->rank << h->n_local;
+  k_collapse<<<grid_for(h->dim_local), kThreads, 0, h->stream>>>(h->psi, h->dim_local, base, pmask, pwant, f);
+  CUDA_TRY(cudaGetLastError());
+  count_pass(h, h->dim_local);
+  return QCSIM_OK;
+}
+
+int engine_save(qcsim_sv* h) {
+  QCSIM_TRY(engine_canonicalize(h));
+  if (!h->saved) CUDA_TRY(cudaMalloc(&h->saved, h->dim_local * sizeof(amp)));
+  CUDA_TRY(cudaMemcpyAsync(h->saved, h->psi, h->dim_local * sizeof(amp), cudaMemcpyDeviceToDevice, h->stream));
+  return QCSIM_OK;
+}
+
+int engine_restore(qcsim_sv* h, bool destructive) {
+  if (!h->saved) return QCSIM_OK;  // QubitRegister.h:607,613
+  if (h->world > 1) dist_reset_layout(h);
+  if (destructive) {
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    std::swap(h->psi, h->saved);
+    CUDA_TRY(cudaFree(h->saved));
+    h->saved = nullptr;
+    if (h->world > 1) QCSIM_TRY(dist_buffers_changed(h));
+  } else {
+    CUDA_TRY(cudaMemcpyAsync(h->psi, h->saved, h->dim_local * sizeof(amp), cudaMemcpyDeviceToDevice, h->stream));
+  }
+  return QCSIM_OK;
+}
+
+int engine_inner_product(qcsim_sv* a, qcsim_sv* b, double* re_im) {
+  if (a->n != b->n || a->world != b->world || a->device != b->device)
+    return fail(QCSIM_ERR_BAD_ARG, "registers must have the same shape and device");
+  QCSIM_TRY(engine_canonicalize(a));
+  QCSIM_TRY(engine_canonicalize(b));
+  CUDA_TRY(cudaStreamSynchronize(b->stream));
+  const int g = grid_for(a->dim_local);
+  k_inner_product<<<g, kThreads, 0, a->stream>>>(a->psi, b->psi, a->dim_local, a->d_partials);
+  k_final_sum<<<1, kThreads, 0, a->stream>>>(a->d_partials, g, 2, a->d_scalars);
+  CUDA_TRY(cudaGetLastError());
+  a->stats.kernel_launches += 2;
+  double* stage = (double*)a->h_pinned;
+  CUDA_TRY(cudaMemcpyAsync(stage, a->d_scalars, 2 * sizeof(double), cudaMemcpyDeviceToHost, a->stream));
+  CUDA_TRY(cudaStreamSynchronize(a->stream));
+  if (a->world > 1) QCSIM_TRY(dist_allreduce_host(a, stage, 2));
+  re_im[0] = stage[0];
+  re_im[1] = stage[1];
+  return QCSIM_OK;
+}
+
+// ---- gate application: one kernel per op ---------------------------------------------------------
+
+static FixedBits sorted_bits(const int* a, int na, const int* b, int nb) {
+  FixedBits f;
+  f.n = 0;
+  f.pos[0] = f.pos[1] = f.pos[2] = 0;
+  int tmp[6];
+  int n = 0;
+  for (int i = 0; i < na; ++i) tmp[n++] = a[i];
+  for (int i = 0; i < nb; ++i) tmp[n++] = b[i];
+  std::sort(tmp, tmp + n);
+  for (int i = 0; i < n && i < 3; ++i) f.pos[f.n++] = tmp[i];
+  return f;
+}
+
+// Launch `op` on the local slice.  All qubit indices in `op` are PHYSICAL local bit positions.
+int engine_launch_local(qcsim_sv* h, const Op& op) {
+  const int nl = h->n_local;
+  amp* psi = h->psi;
+  uint64_t or_ctrl = 0;
+  for (int i = 0; i < op.n_ctrl; ++i) or_ctrl |= 1ULL << op.ctrl[i];
+  switch (op.kind) {
+    case OP_NOP: return QCSIM_OK;
+    case OP_PAIR: {
+      PairArgs A;
+      A.fix = sorted_bits(op.ctrl, op.n_ctrl, op.tgt, op.n_tgt);
+      if (op.n_tgt == 1) {
+        A.or_lo = or_ctrl;
+        A.or_hi = or_ctrl | (1ULL << op.tgt[0]);
+      } else {
+        A.or_lo = or_ctrl | (1ULL << op.tgt[0]);
+        A.or_hi = or_ctrl | (1ULL << op.tgt[1]);
+      }
+      A.m00 = to_amp(op.m[0]);
+      A.m01 = to_amp(op.m[1]);
+      A.m10 = to_amp(op.m[2]);
+      A.m11 = to_amp(op.m[3]);
+      A.n_items = 1ULL << (nl - A.fix.n);
+      if (op.n_tgt == 1 && op.tgt[0] == 0) {
+        k_pair_q0<<<grid_for(A.n_items / 2 + 1), kThreads, 0, h->stream>>>(psi, A);
+      } else if (A.fix.pos[0] >= 1 && A.n_items >= 2) {
+        k_pair_v2<<<grid_for(A.n_items / 4 + 1), kThreads, 0, h->stream>>>(psi, A);
+      } else {
+        k_pair_v1<<<grid_for(A.n_items), kThreads, 0, h->stream>>>(psi, A);
+      }
+      CUDA_TRY(cudaGetLastError());
+      count_pass(h, 2 * A.n_items);
+      return QCSIM_OK;
+    }
+    case OP_DENSE2: {
+      DenseArgs<2> A;
+      A.fix = sorted_bits(op.ctrl, op.n_ctrl, op.tgt, 2);
+      A.or_ctrl = or_ctrl;
+      for (int j = 0; j < 4; ++j) A.off[j] = ((j & 1) ? (1ULL << op.tgt[0]) : 0) | ((j & 2) ? (1ULL << op.tgt[1]) : 0);
+      for (int j = 0; j < 16; ++j) A.m[j] = to_amp(op.m[j]);
+      A.n_items = 1ULL << (nl - A.fix.n);
+      if (A.fix.pos[0] >= 1 && A.n_items >= 2)
+        k_dense_v2<2><<<grid_for(A.n_items / 2), kThreads, 0, h->stream>>>(psi, A);
+      else
+        k_dense_v1<2><<<grid_for(A.n_items), kThreads, 0, h->stream>>>(psi, A);
+      CUDA_TRY(cudaGetLastError());
+      count_pass(h, 4 * A.n_items);
+      return QCSIM_OK;
+    }
+    case OP_DENSE3: {
+      DenseArgs<3> A;
+      A.fix = sorted_bits(op.ctrl, op.n_ctrl, op.tgt, 3);
+      A.or_ctrl = or_ctrl;
+      for (int j = 0; j < 8; ++j)
+        A.off[j] = ((j & 1) ? (1ULL << op.tgt[0]) : 0) | ((j & 2) ? (1ULL << op.tgt[1]) : 0) | ((j & 4) ? (1ULL << op.tgt[2]) : 0);
+      for (int j = 0; j < 64; ++j) A.m[j] = to_amp(op.m[j]);
+      A.n_items = 1ULL << (nl - A.fix.n);
+      if (A.fix.pos[0] >= 1 && A.n_items >= 2)
+        k_dense_v2<3><<<grid_for(A.n_items / 2), kThreads, 0, h->stream>>>(psi, A);
+      else
+        k_dense_v1<3><<<grid_for(A.n_items), kThreads, 0, h->stream>>>(psi, A);
+      CUDA_TRY(cudaGetLastError());
+      count_pass(h, 8 * A.n_items);
+      return QCSIM_OK;
+    }
+    case OP_DIAG: {
+      DiagArgs A;
+      A.ctrl = sorted_bits(op.ctrl, op.n_ctrl, nullptr, 0);
+      A.or_ctrl = or_ctrl;
+      A.nsel = op.n_tgt;
+      for (int k = 0; k < 3; ++k) A.selpos[k] = k < op.n_tgt ? op.tgt[k] : 0;
+      for (int j = 0; j < 8; ++j) A.table[j] = j < (1 << op.n_tgt) ? to_amp(op.m[j]) : make_amp(1, 0);
+      A.n_items = 1ULL << (nl - A.ctrl.n);
+      if ((A.ctrl.n == 0 || A.ctrl.pos[0] >= 1) && A.n_items >= 2)
+        k_diag_v2<<<grid_for(A.n_items / 4 + 1), kThreads, 0, h->stream>>>(psi, A);
+      else
+        k_diag_v1<<<grid_for(A.n_items), kThreads, 0, h->stream>>>(psi, A);
+      CUDA_TRY(cudaGetLastError());
+      count_pass(h, A.n_items);
+      return QCSIM_OK;
+    }
+  }
+  return fail(QCSIM_ERR_BAD_ARG, "unknown op kind");
+}
+
+int engine_apply_now(qcsim_sv* h, const Op& op) {
+  if (h->world > 1) return dist_apply(h, op);
+  return engine_launch_local(h, op);
+}
+
+int engine_enqueue(qcsim_sv* h, const Op& op) {
+  if (op.kind != OP_NOP) h->queue.push_back(op);
+  if (h->queue.size() >= 4096) return engine_flush(h);
+  return QCSIM_OK;
+}
+
+void engine_drop_queue(qcsim_sv* h) { h->queue.clear(); }
+
+int engine_flush(qcsim_sv* h) {
+  if (h->queue.empty()) return QCSIM_OK;
+  std::vector<Op> q;
+  q.swap(h->queue);
+  return fusion_execute(h, q);
+}
+
+int engine_canonicalize(qcsim_sv* h) {
+  if (h->world > 1) return dist_canonicalize(h);
+  return QCSIM_OK;
+}
+
+// ---- QFT (QuantumFourierTransform.h:35-87, QubitsSwapper.h:23-34) ---------------------------------
+
+static void hadamard_matrix(double* m) {  // SimpleGates.h:588-596
+  const double v = 1. / std::sqrt(2.);
+  const double hm[8] = {v, 0, v, 0, v, 0, -v, 0};
+  std::memcpy(m, hm, sizeof hm);
+}
+static void cphase_matrix(double* m, double theta) {  // QuantumGate.h:251-269, m33 = std::polar(1., theta)
+  std::memset(m, 0, 32 * sizeof(double));
+  m[0] = m[10] = m[20] = 1.0;
+  m[30] = std::cos(theta);
+  m[31] = std::sin(theta);
+}
+static void swap_matrix(double* m) {  // QuantumGate.h:10-28
+  std::memset(m, 0, 32 * sizeof(double));
+  m[0] = 1.0;
+  m[2 * (1 * 4 + 2)] = 1.0;
+  m[2 * (2 * 4 + 1)] = 1.0;
+  m[30] = 1.0;
+}
+
+int engine_qft(qcsim_sv* h, uint64_t sq_, uint64_t eq_, bool do_swap, bool inverse) {
+  // sub-register clamp as in QuantumSubAlgorithmOnSubregister (QuantumAlgorithm.h): eq = max(sq, min(N-1, eq))
+  const uint64_t nm1 = (uint64_t)h->n - 1;
+  if (sq_ > nm1) return fail(QCSIM_ERR_QUBIT_TOO_HIGH, "Qubit number is too high");
+  const int sq = (int)sq_;
+  const int eq = (int)std::max<uint64_t>(sq_, std::min<uint64_t>(nm1, eq_));
+  double hm[8], cp[32], sw[32];
+  hadamard_matrix(hm);
+  swap_matrix(sw);
+  std::vector<Op> ops;
+  auto H = [&](int q) { ops.push_back(classify(1, hm, 0, q, 0, 0)); };
+  auto CP = [&](int q, int c, double phase) {
+    cphase_matrix(cp, phase);
+    ops.push_back(classify(2, cp, QCSIM_GATE_CONTROLLED | QCSIM_GATE_DIAGONAL, q, c, 0));
+  };
+  auto swaps = [&]() {
+    int s = sq, e = eq;
+    while (s < e) {
+      ops.push_back(classify(2, sw, QCSIM_GATE_SWAP, s, e, 0));
+      ++s;
+      --e;
+    }
+  };
+  const double pi_2 = 1.57079632679489661923;  // M_PI_2
+  if (!inverse) {
+    H(eq);
+    for (int cur = eq; cur > sq; --cur) {
+      double phase = pi_2;
+      for (int ctrl = cur - 1; ctrl >= sq; --ctrl) {
+        CP(cur, ctrl, phase);
+        phase *= 0.5;
+      }
+      H(cur - 1);
+    }
+    if (do_swap) swaps();
+  } else {
+    if (do_swap) swaps();
+    for (int cur = sq + 1; cur <= eq; ++cur) {
+      H(cur - 1);
+      double phase = -pi_2;
+      for (int ctrl = cur - 1; ctrl >= sq; --ctrl) {
+        CP(cur, ctrl, phase);
+        phase *= 0.5;
+      }
+    }
+    H(eq);
+  }
+  h->stats.gates_applied += ops.size();
+  if (h->fusion) {
+    for (const Op& op : ops) QCSIM_TRY(engine_enqueue(h, op));
+    return QCSIM_OK;
+  }
+  QCSIM_TRY(engine_flush(h));
+  return fusion_execute(h, ops);
+}
+
+// ---- measurement scan ----------------------------------------------------------------------------
+
+int engine_pick_state(qcsim_sv* h, double prob, uint64_t fallback, uint64_t* outcome) {
+  QCSIM_TRY(engine_canonicalize(h));
+  if (h->world > 1) return dist_pick_state(h, prob, fallback, outcome);
+  const int g = (int)std::min<uint64_t>(h->n_chunks, (uint64_t)kMaxPartials);
+  k_chunk_sums<<<g, kThreads, 0, h->stream>>>(h->psi, h->dim_local, h->n_chunks, h->d_chunk_sums);
+  k_find_chunk<<<1, 1024, 0, h->stream>>>(h->d_chunk_sums, h->n_chunks, dd_make(0, 0), prob, h->d_scan);
+  k_find_in_chunk<<<1, kThreads, 0, h->stream>>>(h->psi, h->dim_local, prob, h->d_scan);
+  CUDA_TRY(cudaGetLastError());
+  h->stats.kernel_launches += 3;
+  h->stats.state_passes += 1;
+  h->stats.bytes_moved += 16ULL * h->dim_local;
+  ScanResult* res = (ScanResult*)h->h_pinned;
+  CUDA_TRY(cudaMemcpyAsync(res, h->d_scan, sizeof(ScanResult), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  uint64_t s = res->found ? res->index : fallback;
+  if (h->strict_measure) {
+    // replay the reference's sequential fp64 sum (QubitRegister.h:172-190) for a bit-identical outcome
+    unsigned long long* d_idx = (unsigned long long*)(h->d_scalars + 8);
+    k_sequential_scan<<<1, kThreads, 0, h->stream>>>(h->psi, h->dim_local, 0.0, prob, d_idx, h->d_scalars + 9);
+    CUDA_TRY(cudaGetLastError());
+    h->stats.kernel_launches += 1;
+    unsigned long long* stage = (unsigned long long*)((char*)h->h_pinned + 1024);
+    CUDA_TRY(cudaMemcpyAsync(stage, d_idx, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    s = (*stage == ~0ULL) ? fallback : (uint64_t)*stage;
+  }
+  *outcome = s;
+  return QCSIM_OK;
+}
+
+int engine_sample(qcsim_sv* h, const double* probs, uint64_t count, uint64_t* outcomes) {
+  // one scan per draw for now; the chunk masses are recomputed each time (state is unchanged)
+  for (uint64_t i = 0; i < count; ++i) QCSIM_TRY(engine_pick_state(h, probs[i], 0, &outcomes[i]));
+  return QCSIM_OK;
+}
+
+}  // namespace qcsim

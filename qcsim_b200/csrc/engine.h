@@ -1,0 +1,99 @@
+// engine.h -- the register object behind the C ABI and the host-side engine entry points.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/qcsim_b200.h"
+#include "classify.h"
+#include "common.cuh"
+
+namespace qcsim {
+
+extern thread_local std::string g_last_error;
+int fail(int code, const char* fmt, ...);
+
+#define QCSIM_TRY(expr)              \
+  do {                               \
+    const int rc__ = (expr);         \
+    if (rc__ != QCSIM_OK) return rc__; \
+  } while (0)
+
+#define CUDA_TRY(expr)                                                                              \
+  do {                                                                                              \
+    const cudaError_t ce__ = (expr);                                                                \
+    if (ce__ != cudaSuccess)                                                                        \
+      return ::qcsim::fail(ce__ == cudaErrorMemoryAllocation ? QCSIM_ERR_OOM : QCSIM_ERR_CUDA, "%s: %s", #expr, \
+                           cudaGetErrorString(ce__));                                               \
+  } while (0)
+
+struct ScanResult;
+
+}  // namespace qcsim
+
+// The opaque handle of include/qcsim_b200.h.  Replaces the reference's registerStorage /
+// resultsStorage / savedStateStorage host vectors (QubitRegister.h:718-721) with ONE device
+// buffer (all kernels are in place) plus an optional saved copy.
+struct qcsim_sv {
+  int n = 0;             // total qubits
+  int n_local = 0;       // qubits addressed inside this rank's slice
+  uint64_t dim = 0;      // 2^n
+  uint64_t dim_local = 0;
+  int device = 0;
+  int rank = 0, world = 1;
+  cudaStream_t stream = nullptr;
+
+  qcsim::amp* psi = nullptr;
+  qcsim::amp* saved = nullptr;
+
+  // scratch for reductions / scans
+  double* d_partials = nullptr;  // 2 * kMaxPartials doubles
+  double* d_scalars = nullptr;   // small result area
+  qcsim::dd* d_chunk_sums = nullptr;
+  uint64_t n_chunks = 0;
+  qcsim::ScanResult* d_scan = nullptr;
+  void* h_pinned = nullptr;      // 4 KiB pinned staging for scalar results
+
+  bool fusion = false;
+  bool strict_measure = false;
+  std::vector<qcsim::Op> queue;  // deferred gates (fusion mode / apply_batch)
+
+  void* nccl_comm = nullptr;     // ncclComm_t when world > 1
+  void* dist = nullptr;          // sharding state (dist.cu)
+
+  qcsim_stats stats = {};
+};
+
+namespace qcsim {
+
+int engine_create(qcsim_sv** out, int n_qubits, int device, int rank, int world, const void* nccl_id);
+int engine_nccl_unique_id(void* out128);
+int engine_destroy(qcsim_sv* h);
+int engine_clone(const qcsim_sv* src, qcsim_sv** out);
+
+int engine_set_basis_state(qcsim_sv* h, uint64_t state);
+int engine_fill(qcsim_sv* h, double re, double im);
+int engine_set_amplitude(qcsim_sv* h, uint64_t state, double re, double im);
+int engine_get_amplitude(qcsim_sv* h, uint64_t state, double* re_im);
+int engine_transfer(qcsim_sv* h, double* host, uint64_t first, uint64_t count, bool to_device);
+int engine_masked_norm2(qcsim_sv* h, uint64_t mask, uint64_t want, double* out);
+int engine_scale(qcsim_sv* h, double f);
+int engine_collapse(qcsim_sv* h, uint64_t mask, uint64_t want, double f);
+int engine_save(qcsim_sv* h);
+int engine_restore(qcsim_sv* h, bool destructive);
+int engine_inner_product(qcsim_sv* a, qcsim_sv* b, double* re_im);
+
+int engine_apply_now(qcsim_sv* h, const Op& op);
+int engine_enqueue(qcsim_sv* h, const Op& op);
+int engine_flush(qcsim_sv* h);
+void engine_drop_queue(qcsim_sv* h);
+int engine_canonicalize(qcsim_sv* h);
+int engine_qft(qcsim_sv* h, uint64_t sq, uint64_t eq, bool do_swap, bool inverse);
+
+int engine_pick_state(qcsim_sv* h, double prob, uint64_t fallback, uint64_t* outcome);
+int engine_sample(qcsim_sv* h, const double* probs, uint64_t count, uint64_t* outcomes);
+
+}  // namespace qcsim
