@@ -1,0 +1,467 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the statevector hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--qubits n] [--workload random|qft]
+
+A "step" is one layer of BASELINE config 2 (30-qubit random circuit: a 1-qubit gate from
+{H, RX, RZ} on every qubit, then 9 CNOT + 4 CCNOT on a random qubit permutation = 43 gate
+applications) applied to the device-resident fp64-complex register.  `value` = gate
+applications per second over the timed K steps (state resident in HBM; one sync at the end);
+`e2e` = the same metric through the public API with HOST inputs every step (the layer's gate
+descriptors cross the C ABI from host memory) and a device->host read of a result every step.
+N > 1: one process per GPU (torchrun), the register is sharded on its top log2(N) qubits and
+grows by log2(N) qubits (weak scaling: per-GPU slice fixed).
+
+`--impl reference` times the reference's own CPU implementation (oracle/_ref, the unmodified
+QCSim headers compiled with OpenMP; else the C port) on the host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "gate_apps_per_s"
+UNIT = "gate-apps/s"
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0=None, t1=None):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        for ts, line in self.lines:
+            if t0 is not None and not (t0 - 0.05 <= ts <= t1 + 0.15):
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power)}
+
+
+# --------------------------------------------------------------------------------------------------
+# workloads
+# --------------------------------------------------------------------------------------------------
+def make_layers(n, count, workload):
+    from qcsim_b200 import circuits
+
+    if workload == "random":
+        rng = circuits.SplitMix64(circuits.RANDOM_CIRCUIT_SEED)
+        return [circuits.random_layer(n, rng) for _ in range(count)]
+    # qft: a step is one full QFT of the register (BASELINE config 3 / 5)
+    return [circuits.qft_circuit(n) for _ in range(count)]
+
+
+def pack_gates(layer):
+    import numpy as np
+
+    from qcsim_b200 import _lib
+
+    arr = (_lib.GateStruct * len(layer))()
+    for i, (g, q, c1, c2) in enumerate(layer):
+        arr[i].nq, arr[i].flags, arr[i].q, arr[i].c1, arr[i].c2 = g.nq, g.flags, q, c1, c2
+        flat = np.ascontiguousarray(g.matrix, dtype=np.complex128).view(np.float64).ravel()
+        C.memmove(arr[i].m, flat.ctypes.data, flat.nbytes)
+    return arr
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import qcsim_b200
+    from qcsim_b200 import _lib
+    from qcsim_b200.sharded import create_register
+
+    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; qcsim_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = _lib.load()
+
+    log2w = world.bit_length() - 1
+    n = args.qubits + log2w  # weak scaling: 2^qubits amplitudes per GPU
+    K, W = args.steps, args.warmup
+    layers = make_layers(n, K + W, args.workload)
+    packed = [pack_gates(l) for l in layers]
+    gates_per_step = len(layers[0])
+    h2d_per_step = C.sizeof(_lib.GateStruct) * gates_per_step
+
+    reg = create_register(n, local_rank, rank, world, dist if world > 1 else None)
+    h = reg._h
+    if args.fusion:
+        reg.set_fusion(True)
+    dptr, sptr = C.c_void_p(), C.c_void_p()
+    _lib.check(lib.qcsim_sv_device_ptr(h, C.byref(dptr), C.byref(sptr)))
+    stream = torch.cuda.ExternalStream(sptr.value, device=torch.device("cuda", local_rank))
+
+    def barrier():
+        reg.sync()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def apply_step(i):
+        _lib.check(lib.qcsim_sv_apply_batch(h, packed[i], gates_per_step))
+
+    def timed(fn_steps):
+        """K steps bracketed by barrier + synchronize, CUDA events on the engine's stream, max over ranks."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        e0.record(stream)
+        fn_steps()
+        reg.flush()  # submit any fused queue so e1 is recorded right after the last kernel
+        e1.record(stream)
+        barrier()
+        t1 = time.time()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, t0, t1
+
+    # ---- device-resident leg -----------------------------------------------------------------
+    for i in range(W):
+        apply_step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    reg.reset_stats()
+    ms, t0, t1 = timed(lambda: [apply_step(W + i) for i in range(K)])
+    st = reg.stats()
+    clocks = sampler.stop(t0, t1)
+    total_gates = gates_per_step * K
+    value = total_gates / (ms * 1e-3)
+    norm2 = reg.norm2()
+
+    # ---- end-to-end leg: host gate descriptors in, one double out, every step ----------------
+    out = C.c_double()
+    e2e_q = 0
+
+    def e2e_steps():
+        for i in range(K):
+            apply_step(W + i)
+            _lib.check(lib.qcsim_sv_qubit_probability(h, e2e_q, C.byref(out)))
+
+    apply_step(0)
+    _lib.check(lib.qcsim_sv_qubit_probability(h, e2e_q, C.byref(out)))
+    ms_e2e, _, _ = timed(e2e_steps)
+    e2e_value = total_gates / (ms_e2e * 1e-3)
+
+    # ---- roofline of the dominant kernel, measured live ---------------------------------------
+    peak, peak_src = load_peaks()
+    algo_bytes = st["bytes_moved"]  # 32 B x amplitudes touched, summed over the timed passes (this rank)
+    achieved = algo_bytes / (ms * 1e-3) / 1e9
+    kernels = {}
+    if rank == 0 and not args.no_kernel_sweep:
+        kernels = kernel_sweep(reg, lib, h, stream, n - log2w, torch)
+    roofline = {
+        "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+        "traffic": None, "peak_source": peak_src,
+        "kernel": "fused gate-block passes (k_tile_block)" if args.fusion else "single-gate passes (k_pair_v2 dominant)",
+        "bytes_per_step": algo_bytes // max(K, 1), "passes_per_step": st["state_passes"] / max(K, 1),
+        "nominal_peak_frac": round(achieved / 8000.0, 4),
+    }
+
+    result = {
+        "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": round(ms / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{n}-qubit {'random circuit layer (H/RX/RZ + 9 CNOT + 4 CCNOT)' if args.workload == 'random' else 'QFT'}",
+                   "qubits": n, "qubits_per_gpu": n - log2w, "gate_apps_per_step": gates_per_step,
+                   "state_bytes_per_gpu": 16 << (n - log2w), "parallelism": f"shard{world}" if world > 1 else "single",
+                   "fusion": bool(args.fusion), "l2": "inputs_exceed_l2 (state >> 126 MB)", "seed": 20260117},
+        "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d_per_step, "d2h_bytes_per_step": 8,
+                "ms_per_step": round(ms_e2e / K, 4)},
+        "gpu_launches": int(st["kernel_launches"]),
+        "clocks": clocks,
+        "roofline": roofline,
+        "kernels": kernels,
+        "check": {"norm2": norm2},
+        "exchange": {"calls": st["exchange_calls"], "bytes": st["exchange_bytes"], "ms": st["exchange_ms"]},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        result["cpu_baseline"] = cpu_baseline(args.qubits, args.workload, budget_s=args.cpu_budget)
+    reg.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(result), flush=True)
+
+
+def kernel_sweep(reg, lib, h, stream, n_local, torch):
+    """Isolated per-kernel HBM numbers (CUDA events on the engine stream, 3 warm-up + 10 timed)."""
+    import numpy as np
+
+    from qcsim_b200 import _lib, gates
+
+    peak, _ = load_peaks()
+    was_fused = False
+    _lib.check(lib.qcsim_sv_set_fusion(h, 0))
+    cases = {
+        "H q=0": (gates.HadamardGate(), (0, 0, 0), 32), "H q=1": (gates.HadamardGate(), (1, 0, 0), 32),
+        "H q=mid": (gates.HadamardGate(), (n_local // 2, 0, 0), 32), "H q=top": (gates.HadamardGate(), (n_local - 1, 0, 0), 32),
+        "RZ q=mid": (gates.RzGate(0.3), (n_local // 2, 0, 0), 32),
+        "CNOT t=mid c=top": (gates.CNOTGate(), (n_local // 2, n_local - 1, 0), 16),
+        "CNOT t=top c=0": (gates.CNOTGate(), (n_local - 1, 0, 0), 16),
+        "CPhase t=top c=mid": (gates.ControlledPhaseShiftGate(0.1), (n_local - 1, n_local // 2, 0), 8),
+        "SWAP 0,top": (gates.SwapGate(), (0, n_local - 1, 0), 16),
+        "CCX t=3 c=mid,top": (gates.ToffoliGate(), (3, n_local // 2, n_local - 1), 8),
+        "dense 4x4 mid,top": (gates.AppliedGate(np.linalg.qr(np.random.default_rng(1).standard_normal((4, 4)) + 1j)[0]), (n_local // 2, n_local - 1, 0), 32),
+        "dense 8x8 0,mid,top": (gates.AppliedGate(np.linalg.qr(np.random.default_rng(2).standard_normal((8, 8)) + 1j)[0]), (0, n_local // 2, n_local - 1), 32),
+    }
+    out = {}
+    for name, (g, qs, bytes_per_amp) in cases.items():
+        m = np.ascontiguousarray(g.matrix, dtype=np.complex128)
+        ptr = m.ctypes.data_as(C.c_void_p)
+        for _ in range(3):
+            _lib.check(lib.qcsim_sv_apply(h, g.nq, ptr, g.flags, *qs))
+        reg.sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        e0.record(stream)
+        for _ in range(reps):
+            _lib.check(lib.qcsim_sv_apply(h, g.nq, ptr, g.flags, *qs))
+        e1.record(stream)
+        reg.sync()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        gbs = bytes_per_amp * (1 << n_local) / (ms * 1e-3) / 1e9
+        out[name] = {"ms": round(ms, 4), "algo_bytes_per_amp": bytes_per_amp, "GBps": round(gbs, 1), "frac_of_peak": round(gbs / peak, 4)}
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU baseline / reference arm
+# --------------------------------------------------------------------------------------------------
+def _host_mem_gib():
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable"):
+                return int(line.split()[1]) / (1 << 20)
+    except Exception:
+        pass
+    return 8.0
+
+
+def _cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def _pick_cpu_qubits(n_target):
+    # the CPU path needs 2 x 16 x 2^n bytes (register + scratch, QubitRegister.h:718-719)
+    avail = _host_mem_gib()
+    n = n_target
+    while n > 16 and (32 << n) / (1 << 30) > 0.6 * avail:
+        n -= 1
+    return n
+
+
+def _stratified_sample(layer, k):
+    """every (len/k)-th gate of the layer: keeps the 1q : CNOT : CCNOT mix"""
+    if k >= len(layer):
+        return list(layer)
+    step = len(layer) / k
+    return [layer[int(i * step)] for i in range(k)]
+
+
+def cpu_baseline(n_target, workload, budget_s=20.0, variant="avx2"):
+    import oracle
+
+    n = _pick_cpu_qubits(n_target)
+    # keep the first-touch of 2 x 16 x 2^n bytes and a handful of gates inside the budget
+    if n > 28 and budget_s < 60:
+        n = 28
+    if not oracle.ref_available(variant):
+        variant = "sse2"
+    sim = oracle.best_oracle(n, variant)
+    threads = sim.num_threads()
+    layers = make_layers(n, 4, workload)
+    sample = _stratified_sample(layers[0], 11) if workload == "random" else layers[0][:: max(1, len(layers[0]) // 24)]
+    sim.apply(*sample[0])  # warm-up / first touch
+    done, t0 = 0, time.perf_counter()
+    li = 0
+    while True:
+        for g in sample:
+            sim.apply(*g)
+            done += 1
+        li += 1
+        if time.perf_counter() - t0 > budget_s or li >= 50:
+            break
+        sample = _stratified_sample(layers[li % len(layers)], 11) if workload == "random" else sample
+    dt = time.perf_counter() - t0
+    sim.close()
+    rate = done / dt
+    scale = 2.0 ** (n - n_target)  # per-gate cost doubles per qubit (memory-bound full passes)
+    return {"value": round(rate * scale, 4), "unit": UNIT, "cores": threads, "kind": sim.kind,
+            "sample": f"{done} gate applications (stratified 11-of-43 per layer: 1q/CNOT/CCNOT mix) at {n} qubits in {dt:.1f} s "
+                      f"= {rate:.2f}/s measured, scaled x2^({n}-{n_target}) to {n_target} qubits; build=-O2 -fopenmp -m{variant}; cpu={_cpu_model()}",
+            "measured_value_at_sample_size": round(rate, 4), "sample_qubits": n}
+
+
+def run_reference(args):
+    """Reference arm: the reference's own CPU implementation, rank 0 only."""
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return
+    import oracle
+
+    n_target = args.qubits + (max(args.gpus, 1).bit_length() - 1)
+    K, W = args.steps, args.warmup
+    n = _pick_cpu_qubits(n_target)
+    variant = "avx2" if oracle.ref_available("avx2") else "sse2"
+    # calibrate at a small size, then choose (n, gates per step) so K + W steps fit ~150 s
+    budget = 150.0
+    with oracle.best_oracle(22, variant) as cal:
+        lay = make_layers(22, 1, args.workload)[0]
+        smp = _stratified_sample(lay, 11)
+        cal.apply(*smp[0])
+        t0 = time.perf_counter()
+        for g in smp:
+            cal.apply(*g)
+        per_gate_22 = (time.perf_counter() - t0) / len(smp)
+    while n > 22 and per_gate_22 * 2.0 ** (n - 22) * (K + W) > budget:
+        n -= 1
+    gates_per_step = int(max(1, min(11, budget / ((K + W) * per_gate_22 * 2.0 ** (n - 22)))))
+    sim = oracle.best_oracle(n, variant)
+    threads = sim.num_threads()
+    layers = make_layers(n, K + W, args.workload)
+    samples = [_stratified_sample(l, gates_per_step) for l in layers]
+    for i in range(W):
+        for g in samples[i]:
+            sim.apply(*g)
+    t0 = time.perf_counter()
+    done = 0
+    for i in range(K):
+        for g in samples[W + i]:
+            sim.apply(*g)
+            done += 1
+    dt = time.perf_counter() - t0
+    sim.close()
+    rate = done / dt
+    scale = 2.0 ** (n - n_target)
+    value = rate * scale
+    sample = (f"{gates_per_step} of {len(layers[0])} gate applications per step (stratified) at {n} qubits, {done} in {dt:.1f} s = {rate:.3f}/s "
+              f"measured, scaled x2^({n}-{n_target}) to {n_target} qubits; build=-O2 -fopenmp -m{variant}; cpu={_cpu_model()}")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
+        "ms_per_step": round(dt / K * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"{n_target}-qubit random circuit layer (H/RX/RZ + 9 CNOT + 4 CCNOT)" if args.workload == "random" else f"{n_target}-qubit QFT",
+                   "qubits": n_target, "sample_qubits": n, "gate_apps_per_step": len(layers[0]), "seed": 20260117},
+        "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": threads, "kind": sim.kind, "sample": sample},
+        "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--qubits", type=int, default=30, help="qubits per GPU slice (total = qubits + log2(gpus))")
+    ap.add_argument("--workload", default="random", choices=["random", "qft"])
+    ap.add_argument("--fusion", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernel-sweep", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=20.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

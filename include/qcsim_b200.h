@@ -94,7 +94,8 @@ int qcsim_sv_create_sharded(qcsim_sv** out, int n_qubits, int device, int rank, 
                             const void* nccl_id_128_bytes);
 int qcsim_sv_destroy(qcsim_sv* h);
 int qcsim_sv_clone(const qcsim_sv* src, qcsim_sv** out);
-int qcsim_sv_sync(qcsim_sv* h);
+int qcsim_sv_sync(qcsim_sv* h);  /* flush queued gates and wait for the stream */
+int qcsim_sv_flush(qcsim_sv* h); /* submit queued gates to the stream without waiting */
 int qcsim_sv_n_qubits(const qcsim_sv* h, int* n_qubits, int* n_local_qubits);
 /* raw device pointer / stream of the local slice, for zero-copy interop (e.g. torch.from_blob) */
 int qcsim_sv_device_ptr(qcsim_sv* h, void** dptr, void** cuda_stream);

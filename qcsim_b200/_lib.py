@@ -63,6 +63,7 @@ SIGNATURES = {
     "qcsim_sv_destroy": (C.c_int, [_P]),
     "qcsim_sv_clone": (C.c_int, [_P, C.POINTER(_P)]),
     "qcsim_sv_sync": (C.c_int, [_P]),
+    "qcsim_sv_flush": (C.c_int, [_P]),
     "qcsim_sv_n_qubits": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "qcsim_sv_device_ptr": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P)]),
     "qcsim_sv_set_basis_state": (C.c_int, [_P, _U64]),

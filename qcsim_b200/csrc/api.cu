@@ -79,6 +79,11 @@ int qcsim_sv_sync(qcsim_sv* h) {
   return QCSIM_OK;
 }
 
+int qcsim_sv_flush(qcsim_sv* h) {
+  API_GUARD(h);
+  return engine_flush(h);
+}
+
 int qcsim_sv_n_qubits(const qcsim_sv* h, int* n_qubits, int* n_local_qubits) {
   if (!h) return fail(QCSIM_ERR_BAD_ARG, "null register handle");
   if (n_qubits) *n_qubits = h->n;

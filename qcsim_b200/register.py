@@ -319,6 +319,9 @@ class QubitRegister:
     def set_strict_measure(self, enabled: bool) -> None:
         _lib.check(self._lib.qcsim_sv_set_strict_measure(self._h, int(enabled)))
 
+    def flush(self) -> None:
+        _lib.check(self._lib.qcsim_sv_flush(self._h))
+
     def sync(self) -> None:
         _lib.check(self._lib.qcsim_sv_sync(self._h))
 
