@@ -1,5 +1,6 @@
 // dist.cu -- sharded registers (placeholder until the NCCL / peer-memory exchange lands).
 #include "dist.h"
+#include "fusion.h"
 
 namespace qcsim {
 
@@ -16,6 +17,8 @@ int dist_allreduce_host(qcsim_sv*, double*, int) { return QCSIM_OK; }
 int dist_apply(qcsim_sv*, const Op&) { return fail(QCSIM_ERR_UNSUPPORTED, "sharded registers are not built yet"); }
 int dist_canonicalize(qcsim_sv*) { return QCSIM_OK; }
 int dist_pick_state(qcsim_sv*, double, uint64_t, uint64_t*) { return fail(QCSIM_ERR_UNSUPPORTED, "sharded registers are not built yet"); }
+
+int dist_execute(qcsim_sv*, const std::vector<Op>&) { return fail(QCSIM_ERR_UNSUPPORTED, "sharded registers are not built yet"); }
 
 int engine_nccl_unique_id(void* out) { return dist_unique_id(out); }
 

@@ -1,11 +1,393 @@
-// fusion.cu -- see fusion.h
+// fusion.cu -- gate-stream planner and launcher for fused gate blocks (see fusion.h, tile_kernels.cuh).
+//
+// Planning is greedy and order-preserving:
+//   * walk the pending ops in program order and grow a tile-qubit set T (low L qubits fixed);
+//     an op is absorbed into the current pass when its non-diagonal targets fit into T and it
+//     commutes with every op that was skipped before it (two ops commute when, on every qubit
+//     they share, both act diagonally -- as a control or a diagonal selector);
+//   * absorbed ops keep their relative order and are cut into rounds of <= 3 target bits;
+//   * a pass that would not save HBM traffic over running its ops one by one is not fused.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
 #include "fusion.h"
+#include "tile_kernels.cuh"
 
 namespace qcsim {
 
-int fusion_execute(qcsim_sv* h, const std::vector<Op>& ops) {
-  for (const Op& op : ops) QCSIM_TRY(engine_apply_now(h, op));
+namespace {
+
+struct OpMasks {
+  uint64_t nd;  // qubits acted on non-diagonally (must be tile qubits)
+  uint64_t dg;  // qubits acted on diagonally (controls, diagonal selectors): anywhere
+};
+
+OpMasks masks_of(const Op& op) {
+  OpMasks m{0, 0};
+  for (int i = 0; i < op.n_ctrl; ++i) m.dg |= 1ULL << op.ctrl[i];
+  for (int i = 0; i < op.n_tgt; ++i) (op.kind == OP_DIAG ? m.dg : m.nd) |= 1ULL << op.tgt[i];
+  return m;
+}
+
+// HBM bytes per amplitude of the state if the op runs as its own kernel
+double standalone_cost(const Op& op) {
+  int fixed_low = 0;
+  double frac = 1.0;
+  for (int i = 0; i < op.n_ctrl; ++i) {
+    // a control below bit 1 cannot skip sectors (32 B = 2 amplitudes)
+    if (op.ctrl[i] >= 1) frac *= 0.5;
+    else fixed_low++;
+  }
+  if (op.kind == OP_PAIR && op.n_tgt == 2) frac *= 0.5;
+  (void)fixed_low;
+  return 32.0 * frac;
+}
+
+int desc_bytes_of(const Op& op) {
+  int pool = 0;
+  switch (op.kind) {
+    case OP_PAIR: pool = 4; break;
+    case OP_DENSE2: pool = 16; break;
+    case OP_DENSE3: pool = 64; break;
+    case OP_DIAG: pool = 8; break;
+    default: break;
+  }
+  return (int)sizeof(TileOp) + pool * (int)sizeof(amp);
+}
+
+struct PassPlan {
+  std::vector<int> tile;   // tile qubits ascending
+  std::vector<int> ops;    // indices into the op list, program order
+};
+
+int env_int(const char* name, int dflt) {
+  const char* s = std::getenv(name);
+  return s ? std::atoi(s) : dflt;
+}
+
+}  // namespace
+
+// Build the device descriptor for one pass and launch it.
+static int launch_pass(qcsim_sv* h, const std::vector<Op>& all, const PassPlan& plan, unsigned char* host_stage,
+                       unsigned char* dev_stage, size_t* stage_off, size_t stage_cap, int L) {
+  const int k = (int)plan.tile.size();
+  int local_of[64];
+  for (int q = 0; q < 64; ++q) local_of[q] = -1;
+  for (int j = 0; j < k; ++j) local_of[plan.tile[j]] = j;
+
+  std::vector<TileRound> rounds;
+  std::vector<TileOp> tops;
+  std::vector<amp> pool;
+
+  auto finish_round = [&](TileRound& rd, int nrb) {
+    // pad to exactly kRoundBits distinct ascending local bits
+    int bits[4];
+    int n = nrb;
+    for (int i = 0; i < nrb; ++i) bits[i] = rd.rb[i];
+    for (int cand = 0; n < kRoundBits && cand < k; ++cand) {
+      bool used = false;
+      for (int i = 0; i < n; ++i) used |= (bits[i] == cand);
+      if (!used) bits[n++] = cand;
+    }
+    std::sort(bits, bits + n);
+    for (int i = 0; i < n; ++i) rd.rb[i] = bits[i];
+  };
+
+  // ---- cut into rounds: greedy on the union of target bits
+  struct Pending {
+    int op;
+    int lt[3];
+    int nlt;
+  };
+  std::vector<std::vector<Pending>> round_ops;
+  std::vector<std::vector<int>> round_bits;
+  {
+    std::vector<Pending> cur;
+    std::vector<int> bits;
+    for (int idx : plan.ops) {
+      const Op& op = all[idx];
+      Pending p;
+      p.op = idx;
+      p.nlt = 0;
+      if (op.kind != OP_DIAG)
+        for (int i = 0; i < op.n_tgt; ++i) p.lt[p.nlt++] = local_of[op.tgt[i]];
+      std::vector<int> u = bits;
+      for (int i = 0; i < p.nlt; ++i)
+        if (std::find(u.begin(), u.end(), p.lt[i]) == u.end()) u.push_back(p.lt[i]);
+      if ((int)u.size() > kRoundBits) {
+        round_ops.push_back(cur);
+        round_bits.push_back(bits);
+        cur.clear();
+        bits.clear();
+        for (int i = 0; i < p.nlt; ++i) bits.push_back(p.lt[i]);
+      } else {
+        bits = u;
+      }
+      cur.push_back(p);
+    }
+    if (!cur.empty()) {
+      round_ops.push_back(cur);
+      round_bits.push_back(bits);
+    }
+  }
+
+  for (size_t r = 0; r < round_ops.size(); ++r) {
+    TileRound rd;
+    std::memset(&rd, 0, sizeof rd);
+    const int nrb = (int)round_bits[r].size();
+    for (int i = 0; i < nrb; ++i) rd.rb[i] = round_bits[r][i];
+    finish_round(rd, nrb);
+    int reg_of[16];
+    for (int j = 0; j < 16; ++j) reg_of[j] = -1;
+    for (int i = 0; i < kRoundBits; ++i) reg_of[rd.rb[i]] = i;
+    rd.op_begin = (int)tops.size();
+    for (const Pending& p : round_ops[r]) {
+      const Op& op = all[p.op];
+      TileOp t;
+      std::memset(&t, 0, sizeof t);
+      t.moff = (int)pool.size();
+      // controls: round bit / other tile bit / outside the tile
+      for (int i = 0; i < op.n_ctrl; ++i) {
+        const int q = op.ctrl[i];
+        const int lb = local_of[q];
+        if (lb < 0) t.gctrl |= 1ULL << q;
+        else if (reg_of[lb] >= 0) t.rctrl |= 1u << reg_of[lb];
+        else t.lctrl |= 1u << lb;
+      }
+      auto push = [&](const cplx& z) { pool.push_back(make_amp(z.real(), z.imag())); };
+      switch (op.kind) {
+        case OP_PAIR:
+          if (op.n_tgt == 1) {
+            t.kind = TK_PAIR1;
+            t.r0 = reg_of[p.lt[0]];
+            for (int i = 0; i < 4; ++i) push(op.m[i]);
+          } else {
+            t.kind = TK_PAIR2;
+            int a = reg_of[p.lt[0]], b = reg_of[p.lt[1]];
+            if (a < b) {
+              t.r0 = a;
+              t.r1 = b;
+              for (int i = 0; i < 4; ++i) push(op.m[i]);
+            } else {  // swap the roles of the two amplitudes of the pair
+              t.r0 = b;
+              t.r1 = a;
+              push(op.m[3]);
+              push(op.m[2]);
+              push(op.m[1]);
+              push(op.m[0]);
+            }
+          }
+          break;
+        case OP_DENSE2: {
+          t.kind = TK_DENSE2;
+          int a = reg_of[p.lt[0]], b = reg_of[p.lt[1]];
+          const bool flip = a > b;  // matrix bit0 <-> r0, bit1 <-> r1 with r0 < r1
+          t.r0 = flip ? b : a;
+          t.r1 = flip ? a : b;
+          auto perm = [&](int i) { return flip ? (((i & 1) << 1) | ((i >> 1) & 1)) : i; };
+          for (int r2 = 0; r2 < 4; ++r2)
+            for (int c = 0; c < 4; ++c) push(op.m[perm(r2) * 4 + perm(c)]);
+          break;
+        }
+        case OP_DENSE3: {
+          t.kind = TK_DENSE3;
+          int rr[3] = {reg_of[p.lt[0]], reg_of[p.lt[1]], reg_of[p.lt[2]]};
+          // register index x has bit rr[j] <-> matrix bit j
+          auto perm = [&](int x) {
+            int mi = 0;
+            for (int j = 0; j < 3; ++j)
+              if ((x >> rr[j]) & 1) mi |= 1 << j;
+            return mi;
+          };
+          for (int r2 = 0; r2 < 8; ++r2)
+            for (int c = 0; c < 8; ++c) push(op.m[perm(r2) * 8 + perm(c)]);
+          break;
+        }
+        case OP_DIAG: {
+          t.kind = TK_DIAG;
+          t.nsel = op.n_tgt;
+          for (int i = 0; i < op.n_tgt; ++i) {
+            const int q = op.tgt[i];
+            const int lb = local_of[q];
+            if (lb < 0) {
+              t.sel_src[i] = 2;
+              t.sel_pos[i] = q;
+            } else if (reg_of[lb] >= 0) {
+              t.sel_src[i] = 0;
+              t.sel_pos[i] = reg_of[lb];
+            } else {
+              t.sel_src[i] = 1;
+              t.sel_pos[i] = lb;
+            }
+          }
+          for (int i = 0; i < 8; ++i) push(i < (1 << op.n_tgt) ? op.m[i] : cplx(1, 0));
+          break;
+        }
+        default: break;
+      }
+      tops.push_back(t);
+    }
+    rd.op_end = (int)tops.size();
+    rounds.push_back(rd);
+  }
+
+  // ---- descriptor -> staging -> device
+  const size_t bytes = sizeof(TileRound) * rounds.size() + sizeof(TileOp) * tops.size() + sizeof(amp) * pool.size();
+  const size_t padded = (bytes + 255) & ~size_t(255);
+  if (padded > (size_t)kMaxPassDescBytes + 4096 || *stage_off + padded > stage_cap)
+    return fail(QCSIM_ERR_BAD_ARG, "internal: pass descriptor too large (%zu bytes)", bytes);
+  unsigned char* hp = host_stage + *stage_off;
+  unsigned char* dp = dev_stage + *stage_off;
+  *stage_off += padded;
+  size_t o = 0;
+  std::memcpy(hp + o, rounds.data(), sizeof(TileRound) * rounds.size());
+  o += sizeof(TileRound) * rounds.size();
+  std::memcpy(hp + o, tops.data(), sizeof(TileOp) * tops.size());
+  o += sizeof(TileOp) * tops.size();
+  std::memcpy(hp + o, pool.data(), sizeof(amp) * pool.size());
+  CUDA_TRY(cudaMemcpyAsync(dp, hp, padded, cudaMemcpyHostToDevice, h->stream));
+
+  TilePassArgs A;
+  std::memset(&A, 0, sizeof A);
+  A.k = k;
+  A.n_rounds = (int)rounds.size();
+  A.n_ops = (int)tops.size();
+  A.n_pool = (int)pool.size();
+  for (int j = 0; j < k; ++j) A.tpos[j] = plan.tile[j];
+  A.low_identity = L;
+  A.n_tiles = 1ULL << (h->n_local - k);
+  A.desc = dp;
+  A.desc_bytes = (int)padded;
+  const size_t smem = ((size_t)sizeof(amp) << k) + padded;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(k_tile_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    attr_set = true;
+  }
+  const int ctas_per_sm = smem <= 48 * 1024 ? 4 : 2;
+  const uint64_t grid = std::min<uint64_t>(A.n_tiles, (uint64_t)kNumSMs * ctas_per_sm);
+  k_tile_pass<<<(unsigned)grid, kTileThreads, smem, h->stream>>>(h->psi, A);
+  CUDA_TRY(cudaGetLastError());
+  h->stats.kernel_launches += 1;
+  h->stats.state_passes += 1;
+  h->stats.bytes_moved += 32ULL * h->dim_local;
   return QCSIM_OK;
+}
+
+int fusion_execute(qcsim_sv* h, const std::vector<Op>& ops_in) {
+  if (h->world > 1) return dist_execute(h, ops_in);
+  return fusion_execute_local(h, ops_in);
+}
+
+// All qubit indices in `ops` are physical bit positions of the local slice.
+int fusion_execute_local(qcsim_sv* h, const std::vector<Op>& ops) {
+  const int nl = h->n_local;
+  const int N = (int)ops.size();
+  static const int K_env = env_int("QCSIM_TILE_BITS", kMaxTileBits);
+  static const int L_env = env_int("QCSIM_TILE_LOW", 4);
+  static const int no_fuse = env_int("QCSIM_NO_FUSION", 0);
+  const int K = std::max(kRoundBits, std::min({K_env, kMaxTileBits, nl}));
+  const int L = std::max(1, std::min(L_env, K - kRoundBits));
+  if (no_fuse || nl < 6 || N < 2) {
+    for (const Op& op : ops) QCSIM_TRY(engine_launch_local(h, op));
+    return QCSIM_OK;
+  }
+  QCSIM_TRY(fusion_reserve(h));
+
+  std::vector<char> done(N, 0);
+  std::vector<OpMasks> mk(N);
+  for (int i = 0; i < N; ++i) mk[i] = masks_of(ops[i]);
+  const uint64_t all_qubits = (nl >= 64) ? ~0ULL : ((1ULL << nl) - 1ULL);
+  const int WINDOW = 2048;
+  size_t stage_off = 0;
+  int first = 0;
+  while (first < N) {
+    if (done[first] || ops[first].kind == OP_NOP) {
+      done[first] = 1;
+      ++first;
+      continue;
+    }
+    PassPlan plan;
+    uint64_t T = (1ULL << L) - 1ULL;
+    int free_slots = K - L;
+    uint64_t blocked_nd = 0, blocked_d = 0;
+    double saved = 0;
+    int desc = 0;
+    for (int i = first; i < N && i < first + WINDOW; ++i) {
+      if (done[i]) continue;
+      if (ops[i].kind == OP_NOP) continue;
+      const OpMasks& m = mk[i];
+      const bool conflict = ((m.nd | m.dg) & blocked_nd) || (m.nd & blocked_d);
+      if (!conflict) {
+        const uint64_t need = m.nd & ~T;
+        const int c = __builtin_popcountll(need);
+        const int db = desc_bytes_of(ops[i]);
+        if (c <= free_slots && desc + db + (int)sizeof(TileRound) * ((int)plan.ops.size() + 1) <= kMaxPassDescBytes) {
+          T |= need;
+          free_slots -= c;
+          desc += db;
+          plan.ops.push_back(i);
+          saved += standalone_cost(ops[i]);
+          continue;
+        }
+      }
+      blocked_nd |= m.nd;
+      blocked_d |= m.dg;
+      if ((blocked_nd & all_qubits) == all_qubits) break;
+    }
+    if (plan.ops.size() < 2 || saved <= 40.0) {
+      // not worth a fused pass: run the first pending op on its own
+      QCSIM_TRY(engine_launch_local(h, ops[first]));
+      done[first] = 1;
+      ++first;
+      continue;
+    }
+    // pad the tile with the lowest unused qubits
+    for (int q = 0; q < nl && free_slots > 0; ++q)
+      if (!((T >> q) & 1ULL)) {
+        T |= 1ULL << q;
+        --free_slots;
+      }
+    for (int q = 0; q < nl; ++q)
+      if ((T >> q) & 1ULL) plan.tile.push_back(q);
+    // the low run of identity-mapped tile bits may have grown
+    int Lrun = 0;
+    while (Lrun < (int)plan.tile.size() && plan.tile[Lrun] == Lrun) ++Lrun;
+    if (stage_off + kMaxPassDescBytes + 8192 > h->fuse_stage_bytes) {
+      // staging exhausted: wait for the copies queued so far, then reuse it
+      CUDA_TRY(cudaStreamSynchronize(h->stream));
+      stage_off = 0;
+    }
+    QCSIM_TRY(launch_pass(h, ops, plan, (unsigned char*)h->fuse_stage_host, (unsigned char*)h->fuse_stage_dev, &stage_off,
+                          h->fuse_stage_bytes, Lrun));
+    for (int i : plan.ops) done[i] = 1;
+  }
+  // the pinned staging is reused by the next call: its copies must have been consumed
+  CUDA_TRY(cudaEventRecord((cudaEvent_t)h->fuse_stage_event, h->stream));
+  return QCSIM_OK;
+}
+
+int fusion_reserve(qcsim_sv* h) {
+  if (!h->fuse_stage_host) {
+    h->fuse_stage_bytes = 4u << 20;
+    CUDA_TRY(cudaMallocHost(&h->fuse_stage_host, h->fuse_stage_bytes));
+    CUDA_TRY(cudaMalloc(&h->fuse_stage_dev, h->fuse_stage_bytes));
+    cudaEvent_t ev;
+    CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    h->fuse_stage_event = ev;
+    return QCSIM_OK;
+  }
+  CUDA_TRY(cudaEventSynchronize((cudaEvent_t)h->fuse_stage_event));
+  return QCSIM_OK;
+}
+
+void fusion_release(qcsim_sv* h) {
+  if (h->fuse_stage_host) cudaFreeHost(h->fuse_stage_host);
+  if (h->fuse_stage_dev) cudaFree(h->fuse_stage_dev);
+  if (h->fuse_stage_event) cudaEventDestroy((cudaEvent_t)h->fuse_stage_event);
+  h->fuse_stage_host = h->fuse_stage_dev = nullptr;
+  h->fuse_stage_event = nullptr;
 }
 
 }  // namespace qcsim

@@ -12,6 +12,12 @@ namespace qcsim {
 // kernels.  Result is identical (to rounding) to applying the ops one by one.
 int fusion_execute(qcsim_sv* h, const std::vector<Op>& ops);
 
+// same, for ops whose qubit indices are already physical bit positions of the local slice
+int fusion_execute_local(qcsim_sv* h, const std::vector<Op>& ops);
+int fusion_reserve(qcsim_sv* h);
+void fusion_release(qcsim_sv* h);
+int dist_execute(qcsim_sv* h, const std::vector<Op>& ops);
+
 int engine_launch_local(qcsim_sv* h, const Op& op);
 
 }  // namespace qcsim

@@ -285,3 +285,75 @@ def test_grover_with_gates_small():
         k = circuits.grover_iterations(N)
         p_marked = sum(abs(got[marked | (hi << N)]) ** 2 for hi in range(1 << (nq - N)))
         assert abs(p_marked - math.sin((2 * k + 1) * math.asin(2 ** (-N / 2))) ** 2) < 1e-12
+
+
+# ---- fused gate blocks (qcsim_sv_apply_batch / fusion mode) ------------------------------------------
+@pytest.mark.parametrize("mode", ["batch", "fusion"])
+@pytest.mark.parametrize("n,layers", [(6, 4), (9, 5), (13, 6), (16, 6), (21, 3)])
+def test_fused_random_circuit_vs_oracle(n, layers, mode):
+    circ = circuits.random_circuit(n, layers, seed=n * 7 + 1)
+    with oracle.best_oracle(n) as ref, GpuSim(n, fusion=(mode == "fusion"), batch=(mode == "batch")) as gpu:
+        ref.apply_circuit(circ)
+        gpu.apply_circuit(circ)
+        assert maxdiff(gpu.state(), ref.state()) <= TOL
+        assert abs(gpu.norm2() - ref.norm2()) <= TOL
+        st = gpu.reg.stats()
+        if n >= 9:
+            assert st["state_passes"] < len(circ) / 2, st  # really fused
+
+
+@pytest.mark.parametrize("n", [7, 12, 14])
+def test_fused_all_gate_kinds(n):
+    """every gate class (flagged and flag-less) through the tile engine, on rotating qubits, twice
+    with different qubit offsets so targets land on low, tile and out-of-tile positions"""
+    psi0 = random_state(n, 31)
+    circ = []
+    for shift in (0, 3, n - 3):
+        for (g, q, c1, c2) in golden_util.all_gates_circuit(n):
+            circ.append((g, (q + shift) % n, (c1 + shift) % n if g.nq >= 2 else 0, (c2 + shift) % n if g.nq >= 3 else 0))
+    with oracle.best_oracle(n) as ref, GpuSim(n, batch=True) as gpu:
+        ref.set_state(psi0)
+        gpu.set_state(psi0)
+        ref.apply_circuit(circ)
+        gpu.apply_circuit(circ)
+        assert maxdiff(gpu.state(), ref.state()) <= TOL
+
+
+@pytest.mark.parametrize("n", [12, 20])
+def test_fused_qft_vs_oracle(n):
+    psi0 = random_state(n, 3)
+    with oracle.best_oracle(n) as ref, GpuSim(n, fusion=True) as gpu:
+        ref.set_state(psi0)
+        gpu.set_state(psi0)
+        ref.qft()
+        gpu.qft()
+        assert maxdiff(gpu.state(), ref.state()) <= TOL
+        ref.qft(2, n - 3, True, True)
+        gpu.qft(2, n - 3, True, True)
+        assert maxdiff(gpu.state(), ref.state()) <= TOL
+
+
+def test_fused_equals_unfused_large():
+    """24 qubits: fused and one-gate-per-pass execution of the same circuit agree to 1e-13"""
+    n = 24
+    circ = circuits.random_circuit(n, 4) + circuits.qft_circuit(n, 3, 20)
+    with GpuSim(n) as a, GpuSim(n, batch=True) as b:
+        a.apply_circuit(circ)
+        b.apply_circuit(circ)
+        assert maxdiff(a.state(), b.state()) <= 1e-13
+        assert abs(a.norm2() - b.norm2()) <= 1e-13
+
+
+def test_fusion_mode_flushes_on_observation():
+    n = 10
+    circ = circuits.random_circuit(n, 2)
+    with oracle.best_oracle(n) as ref, GpuSim(n, fusion=True) as gpu:
+        for i, g in enumerate(circ):
+            ref.apply(*g)
+            gpu.apply(*g)
+            if i % 17 == 5:
+                assert abs(gpu.qubit_probability(i % n) - ref.qubit_probability(i % n)) <= TOL
+            if i % 29 == 7:
+                p = draws(1, i)[0]
+                assert gpu.measure(0, 2, p) == ref.measure(0, 2, p)
+        assert maxdiff(gpu.state(), ref.state()) <= TOL
