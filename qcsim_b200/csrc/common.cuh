@@ -58,6 +58,20 @@ __device__ __forceinline__ void st_amp(amp* p, amp v) {
   asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
 }
 
+// two adjacent amplitudes moved by one 256-bit LDG/STG (sm_100: LDG.E.ENL2.256)
+struct amp2 {
+  amp a, b;
+};
+__device__ __forceinline__ amp2 ld_amp2(const amp* p) {
+  amp2 r;
+  asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(r.a.x), "=d"(r.a.y), "=d"(r.b.x), "=d"(r.b.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_amp2(amp* p, amp2 v) {
+  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(v.a.x), "d"(v.a.y), "d"(v.b.x), "d"(v.b.y)
+               : "memory");
+}
+
 // ---- double-double (error-free) accumulation, used by the measurement scan -----------------
 struct dd {
   double hi, lo;

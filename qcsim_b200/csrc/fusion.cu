@@ -8,58 +8,17 @@
 //   * absorbed ops keep their relative order and are cut into rounds of <= 3 target bits;
 //   * a pass that would not save HBM traffic over running its ops one by one is not fused.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
 #include "fusion.h"
+#include "planner.h"
 #include "tile_kernels.cuh"
 
 namespace qcsim {
 
 namespace {
-
-struct OpMasks {
-  uint64_t nd;  // qubits acted on non-diagonally (must be tile qubits)
-  uint64_t dg;  // qubits acted on diagonally (controls, diagonal selectors): anywhere
-};
-
-OpMasks masks_of(const Op& op) {
-  OpMasks m{0, 0};
-  for (int i = 0; i < op.n_ctrl; ++i) m.dg |= 1ULL << op.ctrl[i];
-  for (int i = 0; i < op.n_tgt; ++i) (op.kind == OP_DIAG ? m.dg : m.nd) |= 1ULL << op.tgt[i];
-  return m;
-}
-
-// HBM bytes per amplitude of the state if the op runs as its own kernel
-double standalone_cost(const Op& op) {
-  int fixed_low = 0;
-  double frac = 1.0;
-  for (int i = 0; i < op.n_ctrl; ++i) {
-    // a control below bit 1 cannot skip sectors (32 B = 2 amplitudes)
-    if (op.ctrl[i] >= 1) frac *= 0.5;
-    else fixed_low++;
-  }
-  if (op.kind == OP_PAIR && op.n_tgt == 2) frac *= 0.5;
-  (void)fixed_low;
-  return 32.0 * frac;
-}
-
-int desc_bytes_of(const Op& op) {
-  int pool = 0;
-  switch (op.kind) {
-    case OP_PAIR: pool = 4; break;
-    case OP_DENSE2: pool = 16; break;
-    case OP_DENSE3: pool = 64; break;
-    case OP_DIAG: pool = 8; break;
-    default: break;
-  }
-  return (int)sizeof(TileOp) + pool * (int)sizeof(amp);
-}
-
-struct PassPlan {
-  std::vector<int> tile;   // tile qubits ascending
-  std::vector<int> ops;    // indices into the op list, program order
-};
 
 int env_int(const char* name, int dflt) {
   const char* s = std::getenv(name);
@@ -295,73 +254,33 @@ int fusion_execute_local(qcsim_sv* h, const std::vector<Op>& ops) {
   }
   QCSIM_TRY(fusion_reserve(h));
 
-  std::vector<char> done(N, 0);
-  std::vector<OpMasks> mk(N);
-  for (int i = 0; i < N; ++i) mk[i] = masks_of(ops[i]);
-  const uint64_t all_qubits = (nl >= 64) ? ~0ULL : ((1ULL << nl) - 1ULL);
-  const int WINDOW = 2048;
+  const std::vector<PlanStep> steps = plan_passes(ops, nl, K, L, kMaxPassDescBytes, (int)sizeof(TileOp), (int)sizeof(TileRound));
+  static const int debug = env_int("QCSIM_DEBUG_PLAN", 0);
+  if (debug) {
+    int nf = 0, absorbed = 0;
+    for (const PlanStep& st : steps)
+      if (st.fused) {
+        ++nf;
+        absorbed += (int)st.pass.ops.size();
+      }
+    std::fprintf(stderr, "[qcsim plan] %d ops -> %zu steps (%d fused passes holding %d ops), K=%d L=%d\n", N, steps.size(), nf,
+                 absorbed, K, L);
+  }
   size_t stage_off = 0;
-  int first = 0;
-  while (first < N) {
-    if (done[first] || ops[first].kind == OP_NOP) {
-      done[first] = 1;
-      ++first;
+  for (const PlanStep& st : steps) {
+    if (!st.fused) {
+      QCSIM_TRY(engine_launch_local(h, ops[st.pass.ops[0]]));
       continue;
     }
-    PassPlan plan;
-    uint64_t T = (1ULL << L) - 1ULL;
-    int free_slots = K - L;
-    uint64_t blocked_nd = 0, blocked_d = 0;
-    double saved = 0;
-    int desc = 0;
-    for (int i = first; i < N && i < first + WINDOW; ++i) {
-      if (done[i]) continue;
-      if (ops[i].kind == OP_NOP) continue;
-      const OpMasks& m = mk[i];
-      const bool conflict = ((m.nd | m.dg) & blocked_nd) || (m.nd & blocked_d);
-      if (!conflict) {
-        const uint64_t need = m.nd & ~T;
-        const int c = __builtin_popcountll(need);
-        const int db = desc_bytes_of(ops[i]);
-        if (c <= free_slots && desc + db + (int)sizeof(TileRound) * ((int)plan.ops.size() + 1) <= kMaxPassDescBytes) {
-          T |= need;
-          free_slots -= c;
-          desc += db;
-          plan.ops.push_back(i);
-          saved += standalone_cost(ops[i]);
-          continue;
-        }
-      }
-      blocked_nd |= m.nd;
-      blocked_d |= m.dg;
-      if ((blocked_nd & all_qubits) == all_qubits) break;
-    }
-    if (plan.ops.size() < 2 || saved <= 40.0) {
-      // not worth a fused pass: run the first pending op on its own
-      QCSIM_TRY(engine_launch_local(h, ops[first]));
-      done[first] = 1;
-      ++first;
-      continue;
-    }
-    // pad the tile with the lowest unused qubits
-    for (int q = 0; q < nl && free_slots > 0; ++q)
-      if (!((T >> q) & 1ULL)) {
-        T |= 1ULL << q;
-        --free_slots;
-      }
-    for (int q = 0; q < nl; ++q)
-      if ((T >> q) & 1ULL) plan.tile.push_back(q);
-    // the low run of identity-mapped tile bits may have grown
-    int Lrun = 0;
-    while (Lrun < (int)plan.tile.size() && plan.tile[Lrun] == Lrun) ++Lrun;
+    int Lrun = 0;  // the low run of identity-mapped tile bits may be longer than L
+    while (Lrun < (int)st.pass.tile.size() && st.pass.tile[Lrun] == Lrun) ++Lrun;
     if (stage_off + kMaxPassDescBytes + 8192 > h->fuse_stage_bytes) {
       // staging exhausted: wait for the copies queued so far, then reuse it
       CUDA_TRY(cudaStreamSynchronize(h->stream));
       stage_off = 0;
     }
-    QCSIM_TRY(launch_pass(h, ops, plan, (unsigned char*)h->fuse_stage_host, (unsigned char*)h->fuse_stage_dev, &stage_off,
+    QCSIM_TRY(launch_pass(h, ops, st.pass, (unsigned char*)h->fuse_stage_host, (unsigned char*)h->fuse_stage_dev, &stage_off,
                           h->fuse_stage_bytes, Lrun));
-    for (int i : plan.ops) done[i] = 1;
   }
   // the pinned staging is reused by the next call: its copies must have been consumed
   CUDA_TRY(cudaEventRecord((cudaEvent_t)h->fuse_stage_event, h->stream));

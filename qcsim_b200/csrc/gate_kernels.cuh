@@ -23,19 +23,6 @@
 
 namespace qcsim {
 
-struct amp2 {
-  amp a, b;
-};
-__device__ __forceinline__ amp2 ld_amp2(const amp* p) {
-  amp2 r;
-  asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(r.a.x), "=d"(r.a.y), "=d"(r.b.x), "=d"(r.b.y) : "l"(p));
-  return r;
-}
-__device__ __forceinline__ void st_amp2(amp* p, amp2 v) {
-  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(v.a.x), "d"(v.a.y), "d"(v.b.x), "d"(v.b.y)
-               : "memory");
-}
-
 // ------------------------------------------------------------------------------------------------
 // PAIR
 // ------------------------------------------------------------------------------------------------

@@ -1,0 +1,131 @@
+// planner.h -- gate-stream planner for fused gate blocks.  Pure host code (no CUDA), so it is
+// unit-tested on the CPU (tests/test_planner.py compiles it with g++).
+//
+// Input: classified ops (classify.h) whose qubit indices are physical bit positions of the local
+// slice.  Output: an ordered list of steps, each either one op run as its own kernel or a fused
+// pass = (tile qubit set, ops absorbed into it).  Executing the steps in order is equivalent to
+// executing the ops in program order: an op is only moved ahead of a skipped op when the two
+// commute, i.e. on every qubit they share both act diagonally (control or diagonal selector).
+#pragma once
+
+#include <cstdint>
+#include <vector>
+
+#include "classify.h"
+
+namespace qcsim {
+
+struct OpMasks {
+  uint64_t nd;  // qubits acted on non-diagonally (must be tile qubits to be fused)
+  uint64_t dg;  // qubits acted on diagonally (controls, diagonal selectors): may be anywhere
+};
+
+inline OpMasks masks_of(const Op& op) {
+  OpMasks m{0, 0};
+  for (int i = 0; i < op.n_ctrl; ++i) m.dg |= 1ULL << op.ctrl[i];
+  for (int i = 0; i < op.n_tgt; ++i) {
+    if (op.kind == OP_DIAG) m.dg |= 1ULL << op.tgt[i];
+    else m.nd |= 1ULL << op.tgt[i];
+  }
+  return m;
+}
+
+// HBM bytes per amplitude of the state if the op runs as its own kernel (gate_kernels.cuh)
+inline double standalone_cost(const Op& op) {
+  double frac = 1.0;
+  for (int i = 0; i < op.n_ctrl; ++i)
+    if (op.ctrl[i] >= 1) frac *= 0.5;  // a control on bit 0 cannot skip 32-byte sectors
+  if (op.kind == OP_PAIR && op.n_tgt == 2) frac *= 0.5;
+  return 32.0 * frac;
+}
+
+inline int pool_amps_of(const Op& op) {
+  switch (op.kind) {
+    case OP_PAIR: return 4;
+    case OP_DENSE2: return 16;
+    case OP_DENSE3: return 64;
+    case OP_DIAG: return 8;
+    default: return 0;
+  }
+}
+
+struct PassPlan {
+  std::vector<int> tile;  // tile qubits, ascending
+  std::vector<int> ops;   // indices into the op list, program order
+};
+
+struct PlanStep {
+  bool fused;
+  PassPlan pass;  // !fused: pass.ops holds the single op index
+};
+
+// K = tile bits, L = low qubits that are always tile qubits (contiguous 2^L-amplitude runs)
+inline std::vector<PlanStep> plan_passes(const std::vector<Op>& ops, int n_local, int K, int L, int max_desc_bytes,
+                                         int op_bytes, int round_bytes, int window = 2048, double min_saving = 40.0) {
+  const int N = (int)ops.size();
+  std::vector<PlanStep> steps;
+  std::vector<char> done(N, 0);
+  std::vector<OpMasks> mk(N);
+  for (int i = 0; i < N; ++i) mk[i] = masks_of(ops[i]);
+  const uint64_t all_qubits = (n_local >= 64) ? ~0ULL : ((1ULL << n_local) - 1ULL);
+  int first = 0;
+  while (first < N) {
+    if (done[first] || ops[first].kind == OP_NOP) {
+      done[first] = 1;
+      ++first;
+      continue;
+    }
+    PassPlan plan;
+    uint64_t T = (1ULL << L) - 1ULL;
+    int free_slots = K - L;
+    uint64_t blocked_nd = 0, blocked_d = 0;
+    double saved = 0;
+    int desc = 0;
+    for (int i = first; i < N && i < first + window; ++i) {
+      if (done[i] || ops[i].kind == OP_NOP) continue;
+      const OpMasks& m = mk[i];
+      const bool conflict = ((m.nd | m.dg) & blocked_nd) != 0 || (m.nd & blocked_d) != 0;
+      if (!conflict) {
+        const uint64_t need = m.nd & ~T;
+        const int c = __builtin_popcountll(need);
+        const int db = op_bytes + 16 * pool_amps_of(ops[i]);
+        if (c <= free_slots && desc + db + round_bytes * ((int)plan.ops.size() + 1) <= max_desc_bytes) {
+          T |= need;
+          free_slots -= c;
+          desc += db;
+          plan.ops.push_back(i);
+          saved += standalone_cost(ops[i]);
+          continue;
+        }
+      }
+      blocked_nd |= m.nd;
+      blocked_d |= m.dg;
+      if ((blocked_nd & all_qubits) == all_qubits) break;
+    }
+    if (plan.ops.size() < 2 || saved <= min_saving) {
+      // not worth a fused pass: run the first pending op on its own
+      PlanStep s;
+      s.fused = false;
+      s.pass.ops.push_back(first);
+      steps.push_back(s);
+      done[first] = 1;
+      ++first;
+      continue;
+    }
+    for (int q = 0; q < n_local && free_slots > 0; ++q)  // pad the tile with the lowest unused qubits
+      if (!((T >> q) & 1ULL)) {
+        T |= 1ULL << q;
+        --free_slots;
+      }
+    for (int q = 0; q < n_local; ++q)
+      if ((T >> q) & 1ULL) plan.tile.push_back(q);
+    for (int i : plan.ops) done[i] = 1;
+    PlanStep s;
+    s.fused = true;
+    s.pass = plan;
+    steps.push_back(s);
+  }
+  return steps;
+}
+
+}  // namespace qcsim

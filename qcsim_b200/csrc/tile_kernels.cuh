@@ -18,7 +18,6 @@
 #pragma once
 
 #include "common.cuh"
-#include "gate_kernels.cuh"
 
 namespace qcsim {
 
