@@ -27,9 +27,8 @@ int env_int(const char* name, int dflt) {
 
 }  // namespace
 
-// Build the device descriptor for one pass and launch it.
-static int launch_pass(qcsim_sv* h, const std::vector<Op>& all, const PassPlan& plan, unsigned char* host_stage,
-                       unsigned char* dev_stage, size_t* stage_off, size_t stage_cap, int L) {
+// Build the parameter-block descriptor for one pass and launch it.
+static int launch_pass(qcsim_sv* h, const std::vector<Op>& all, const PassPlan& plan, int L) {
   const int k = (int)plan.tile.size();
   int local_of[64];
   for (int q = 0; q < 64; ++q) local_of[q] = -1;
@@ -118,11 +117,16 @@ static int launch_pass(qcsim_sv* h, const std::vector<Op>& all, const PassPlan& 
       switch (op.kind) {
         case OP_PAIR:
           if (op.n_tgt == 1) {
-            t.kind = TK_PAIR1;
+            const cplx *m = op.m;
+            const bool real = m[0].imag() == 0 && m[1].imag() == 0 && m[2].imag() == 0 && m[3].imag() == 0;
+            const bool rim = m[0].imag() == 0 && m[3].imag() == 0 && m[1].real() == 0 && m[2].real() == 0;
+            const bool isx = m[0] == cplx(0, 0) && m[3] == cplx(0, 0) && m[1] == cplx(1, 0) && m[2] == cplx(1, 0);
+            t.kind = isx ? TK_PAIR1_X : real ? TK_PAIR1_REAL : rim ? TK_PAIR1_RIM : TK_PAIR1;
             t.r0 = reg_of[p.lt[0]];
             for (int i = 0; i < 4; ++i) push(op.m[i]);
           } else {
-            t.kind = TK_PAIR2;
+            const bool issw = op.m[0] == cplx(0, 0) && op.m[3] == cplx(0, 0) && op.m[1] == cplx(1, 0) && op.m[2] == cplx(1, 0);
+            t.kind = issw ? TK_PAIR2_SWAP : TK_PAIR2;
             int a = reg_of[p.lt[0]], b = reg_of[p.lt[1]];
             if (a < b) {
               t.r0 = a;
@@ -164,7 +168,7 @@ static int launch_pass(qcsim_sv* h, const std::vector<Op>& all, const PassPlan& 
           break;
         }
         case OP_DIAG: {
-          t.kind = TK_DIAG;
+          t.kind = op.n_tgt == 0 ? TK_PHASE : TK_DIAG;
           t.nsel = op.n_tgt;
           for (int i = 0; i < op.n_tgt; ++i) {
             const int q = op.tgt[i];
@@ -191,42 +195,36 @@ static int launch_pass(qcsim_sv* h, const std::vector<Op>& all, const PassPlan& 
     rounds.push_back(rd);
   }
 
-  // ---- descriptor -> staging -> device
-  const size_t bytes = sizeof(TileRound) * rounds.size() + sizeof(TileOp) * tops.size() + sizeof(amp) * pool.size();
-  const size_t padded = (bytes + 255) & ~size_t(255);
-  if (padded > (size_t)kMaxPassDescBytes + 4096 || *stage_off + padded > stage_cap)
-    return fail(QCSIM_ERR_BAD_ARG, "internal: pass descriptor too large (%zu bytes)", bytes);
-  unsigned char* hp = host_stage + *stage_off;
-  unsigned char* dp = dev_stage + *stage_off;
-  *stage_off += padded;
-  size_t o = 0;
-  std::memcpy(hp + o, rounds.data(), sizeof(TileRound) * rounds.size());
-  o += sizeof(TileRound) * rounds.size();
-  std::memcpy(hp + o, tops.data(), sizeof(TileOp) * tops.size());
-  o += sizeof(TileOp) * tops.size();
-  std::memcpy(hp + o, pool.data(), sizeof(amp) * pool.size());
-  CUDA_TRY(cudaMemcpyAsync(dp, hp, padded, cudaMemcpyHostToDevice, h->stream));
-
-  TilePassArgs A;
-  std::memset(&A, 0, sizeof A);
+  // ---- descriptor -> kernel parameter block
+  if (rounds.size() > (size_t)kMaxTileRounds || tops.size() > (size_t)kMaxTileOps || pool.size() > (size_t)kMaxTilePool)
+    return fail(QCSIM_ERR_BAD_ARG, "internal: pass too large (%zu rounds, %zu ops, %zu pool)", rounds.size(), tops.size(), pool.size());
+  static thread_local TilePassArgs A;  // 12 KiB: keep it off the stack; the launch copies it
   A.k = k;
   A.n_rounds = (int)rounds.size();
-  A.n_ops = (int)tops.size();
-  A.n_pool = (int)pool.size();
-  for (int j = 0; j < k; ++j) A.tpos[j] = plan.tile[j];
   A.low_identity = L;
   A.n_tiles = 1ULL << (h->n_local - k);
-  A.desc = dp;
-  A.desc_bytes = (int)padded;
-  const size_t smem = ((size_t)sizeof(amp) << k) + padded;
+  for (int j = 0; j < kMaxTileBits; ++j) A.tpos[j] = j < k ? plan.tile[j] : 0;
+  for (size_t r = 0; r < rounds.size(); ++r) {
+    A.rounds[r].x = (unsigned)(rounds[r].rb[0] | (rounds[r].rb[1] << 8) | (rounds[r].rb[2] << 16));
+    A.rounds[r].y = (unsigned)(rounds[r].op_begin | (rounds[r].op_end << 16));
+  }
+  for (size_t o = 0; o < tops.size(); ++o) pack_tile_op(tops[o], &A.ops[2 * o]);
+  for (size_t i = 0; i < pool.size(); ++i) A.pool[i] = pool[i];
+  const size_t smem = (size_t)sizeof(amp) << k;
+  static const int variant = env_int("QCSIM_TILE_VARIANT", 0);  // 0: NI=1/128 regs, 1: NI=1/80 regs, 2: NI=2/128 regs
   static bool attr_set = false;
   if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(k_tile_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(k_tile_pass<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(k_tile_pass<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(k_tile_pass<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     attr_set = true;
   }
-  const int ctas_per_sm = smem <= 48 * 1024 ? 4 : 2;
-  const uint64_t grid = std::min<uint64_t>(A.n_tiles, (uint64_t)kNumSMs * ctas_per_sm);
-  k_tile_pass<<<(unsigned)grid, kTileThreads, smem, h->stream>>>(h->psi, A);
+  const int by_smem = std::max(1, (int)((220 * 1024) / (smem + 1024)));
+  const int per_sm = std::min(by_smem, variant == 1 ? 3 : 2);
+  const uint64_t grid = std::min<uint64_t>(A.n_tiles, (uint64_t)kNumSMs * per_sm);
+  if (variant == 2 && k == 12) k_tile_pass<2, 2><<<(unsigned)grid, kTileThreads, smem, h->stream>>>(h->psi, A);
+  else if (variant == 1) k_tile_pass<1, 3><<<(unsigned)grid, kTileThreads, smem, h->stream>>>(h->psi, A);
+  else k_tile_pass<1, 2><<<(unsigned)grid, kTileThreads, smem, h->stream>>>(h->psi, A);
   CUDA_TRY(cudaGetLastError());
   h->stats.kernel_launches += 1;
   h->stats.state_passes += 1;
@@ -252,9 +250,8 @@ int fusion_execute_local(qcsim_sv* h, const std::vector<Op>& ops) {
     for (const Op& op : ops) QCSIM_TRY(engine_launch_local(h, op));
     return QCSIM_OK;
   }
-  QCSIM_TRY(fusion_reserve(h));
 
-  const std::vector<PlanStep> steps = plan_passes(ops, nl, K, L, kMaxPassDescBytes, (int)sizeof(TileOp), (int)sizeof(TileRound));
+  const std::vector<PlanStep> steps = plan_passes(ops, nl, K, L, kMaxTileOps, kMaxTilePool);
   static const int debug = env_int("QCSIM_DEBUG_PLAN", 0);
   if (debug) {
     int nf = 0, absorbed = 0;
@@ -266,7 +263,6 @@ int fusion_execute_local(qcsim_sv* h, const std::vector<Op>& ops) {
     std::fprintf(stderr, "[qcsim plan] %d ops -> %zu steps (%d fused passes holding %d ops), K=%d L=%d\n", N, steps.size(), nf,
                  absorbed, K, L);
   }
-  size_t stage_off = 0;
   for (const PlanStep& st : steps) {
     if (!st.fused) {
       QCSIM_TRY(engine_launch_local(h, ops[st.pass.ops[0]]));
@@ -274,39 +270,12 @@ int fusion_execute_local(qcsim_sv* h, const std::vector<Op>& ops) {
     }
     int Lrun = 0;  // the low run of identity-mapped tile bits may be longer than L
     while (Lrun < (int)st.pass.tile.size() && st.pass.tile[Lrun] == Lrun) ++Lrun;
-    if (stage_off + kMaxPassDescBytes + 8192 > h->fuse_stage_bytes) {
-      // staging exhausted: wait for the copies queued so far, then reuse it
-      CUDA_TRY(cudaStreamSynchronize(h->stream));
-      stage_off = 0;
-    }
-    QCSIM_TRY(launch_pass(h, ops, st.pass, (unsigned char*)h->fuse_stage_host, (unsigned char*)h->fuse_stage_dev, &stage_off,
-                          h->fuse_stage_bytes, Lrun));
+    QCSIM_TRY(launch_pass(h, ops, st.pass, Lrun));
   }
-  // the pinned staging is reused by the next call: its copies must have been consumed
-  CUDA_TRY(cudaEventRecord((cudaEvent_t)h->fuse_stage_event, h->stream));
   return QCSIM_OK;
 }
 
-int fusion_reserve(qcsim_sv* h) {
-  if (!h->fuse_stage_host) {
-    h->fuse_stage_bytes = 4u << 20;
-    CUDA_TRY(cudaMallocHost(&h->fuse_stage_host, h->fuse_stage_bytes));
-    CUDA_TRY(cudaMalloc(&h->fuse_stage_dev, h->fuse_stage_bytes));
-    cudaEvent_t ev;
-    CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    h->fuse_stage_event = ev;
-    return QCSIM_OK;
-  }
-  CUDA_TRY(cudaEventSynchronize((cudaEvent_t)h->fuse_stage_event));
-  return QCSIM_OK;
-}
-
-void fusion_release(qcsim_sv* h) {
-  if (h->fuse_stage_host) cudaFreeHost(h->fuse_stage_host);
-  if (h->fuse_stage_dev) cudaFree(h->fuse_stage_dev);
-  if (h->fuse_stage_event) cudaEventDestroy((cudaEvent_t)h->fuse_stage_event);
-  h->fuse_stage_host = h->fuse_stage_dev = nullptr;
-  h->fuse_stage_event = nullptr;
-}
+int fusion_reserve(qcsim_sv*) { return QCSIM_OK; }
+void fusion_release(qcsim_sv*) {}
 
 }  // namespace qcsim

@@ -60,8 +60,8 @@ struct PlanStep {
 };
 
 // K = tile bits, L = low qubits that are always tile qubits (contiguous 2^L-amplitude runs)
-inline std::vector<PlanStep> plan_passes(const std::vector<Op>& ops, int n_local, int K, int L, int max_desc_bytes,
-                                         int op_bytes, int round_bytes, int window = 2048, double min_saving = 40.0) {
+inline std::vector<PlanStep> plan_passes(const std::vector<Op>& ops, int n_local, int K, int L, int max_ops, int max_pool,
+                                         int window = 2048, double min_saving = 40.0) {
   const int N = (int)ops.size();
   std::vector<PlanStep> steps;
   std::vector<char> done(N, 0);
@@ -80,7 +80,7 @@ inline std::vector<PlanStep> plan_passes(const std::vector<Op>& ops, int n_local
     int free_slots = K - L;
     uint64_t blocked_nd = 0, blocked_d = 0;
     double saved = 0;
-    int desc = 0;
+    int pool = 0;
     for (int i = first; i < N && i < first + window; ++i) {
       if (done[i] || ops[i].kind == OP_NOP) continue;
       const OpMasks& m = mk[i];
@@ -88,11 +88,11 @@ inline std::vector<PlanStep> plan_passes(const std::vector<Op>& ops, int n_local
       if (!conflict) {
         const uint64_t need = m.nd & ~T;
         const int c = __builtin_popcountll(need);
-        const int db = op_bytes + 16 * pool_amps_of(ops[i]);
-        if (c <= free_slots && desc + db + round_bytes * ((int)plan.ops.size() + 1) <= max_desc_bytes) {
+        const int pa = pool_amps_of(ops[i]);
+        if (c <= free_slots && (int)plan.ops.size() < max_ops && pool + pa <= max_pool) {
           T |= need;
           free_slots -= c;
-          desc += db;
+          pool += pa;
           plan.ops.push_back(i);
           saved += standalone_cost(ops[i]);
           continue;

@@ -41,7 +41,7 @@ int hl_plan(const qcsim_gate* gates, int count, int n_local, int K, int L, int* 
     ops.push_back(classify(gates[i].nq, gates[i].m, gates[i].flags, gates[i].q, gates[i].c1, gates[i].c2));
     if (ops_out) export_op(ops.back(), &ops_out[i]);
   }
-  const std::vector<PlanStep> steps = plan_passes(ops, n_local, K, L, 12 * 1024, 64, 32);
+  const std::vector<PlanStep> steps = plan_passes(ops, n_local, K, L, 64, 512);
   int o = 0;
   for (size_t s = 0; s < steps.size(); ++s) {
     step_fused[s] = steps[s].fused ? 1 : 0;
