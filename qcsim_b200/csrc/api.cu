@@ -12,6 +12,7 @@
 
 #include "../../include/qcsim_b200.h"
 #include "engine.h"
+#include "dist.h"
 
 using namespace qcsim;
 
@@ -321,6 +322,7 @@ int qcsim_sv_set_strict_measure(qcsim_sv* h, int enabled) {
 
 int qcsim_sv_get_stats(const qcsim_sv* h, qcsim_stats* out) {
   if (!h || !out) return fail(QCSIM_ERR_BAD_ARG, "null argument");
+  if (h->world > 1) dist_collect_stats(const_cast<qcsim_sv*>(h));
   *out = h->stats;
   return QCSIM_OK;
 }

@@ -1,25 +1,329 @@
-// dist.cu -- sharded registers (placeholder until the NCCL / peer-memory exchange lands).
+// dist.cu -- sharded registers: one process per GPU, state split on the top log2(world) physical
+// index bits.  Planning (which steps are shard-local, when to exchange global and local qubits)
+// is in dist_plan.h; this file executes the plan:
+//   * local steps  -> fusion_execute_local (the same fused / single-gate kernels as one GPU);
+//   * exchange     -> ncclSend/ncclRecv over NVLink among the 2^k ranks that differ in the swapped
+//                     global bits.  The swapped local bits are the top k local positions, so every
+//                     peer's share is one contiguous block: it is sent straight out of the state and
+//                     received into a small double-buffered staging area (the state itself leaves no
+//                     room for a second copy at 33+ qubits per GPU), then copied into place on a
+//                     second stream while the next chunk is on the wire;
+//   * reductions   -> one double(-double) per rank, all-gathered with NCCL, resolved identically
+//                     on every rank.
+#include <nccl.h>
+
+#include <algorithm>
+#include <cstring>
+
 #include "dist.h"
+#include "dist_plan.h"
 #include "fusion.h"
+#include "reduce_kernels.cuh"
 
 namespace qcsim {
 
-int dist_init(qcsim_sv*, const void*) { return fail(QCSIM_ERR_UNSUPPORTED, "sharded registers are not built yet"); }
-void dist_shutdown(qcsim_sv*) {}
-int dist_unique_id(void*) { return fail(QCSIM_ERR_UNSUPPORTED, "sharded registers are not built yet"); }
-void dist_reset_layout(qcsim_sv*) {}
-int dist_buffers_changed(qcsim_sv*) { return QCSIM_OK; }
-void dist_map_mask(qcsim_sv*, uint64_t mask, uint64_t want, uint64_t* pmask, uint64_t* pwant) {
-  *pmask = mask;
-  *pwant = want;
-}
-int dist_allreduce_host(qcsim_sv*, double*, int) { return QCSIM_OK; }
-int dist_apply(qcsim_sv*, const Op&) { return fail(QCSIM_ERR_UNSUPPORTED, "sharded registers are not built yet"); }
-int dist_canonicalize(qcsim_sv*) { return QCSIM_OK; }
-int dist_pick_state(qcsim_sv*, double, uint64_t, uint64_t*) { return fail(QCSIM_ERR_UNSUPPORTED, "sharded registers are not built yet"); }
+#define NCCL_TRY(expr)                                                                            \
+  do {                                                                                            \
+    const ncclResult_t nr__ = (expr);                                                             \
+    if (nr__ != ncclSuccess) return fail(QCSIM_ERR_NCCL, "%s: %s", #expr, ncclGetErrorString(nr__)); \
+  } while (0)
 
-int dist_execute(qcsim_sv*, const std::vector<Op>&) { return fail(QCSIM_ERR_UNSUPPORTED, "sharded registers are not built yet"); }
+namespace {
+
+constexpr uint64_t kStageChunkAmps = 1ULL << 22;  // 64 MiB per peer per buffer
+
+struct DistState {
+  ncclComm_t comm = nullptr;
+  DistLayout layout;
+  cudaStream_t copy_stream = nullptr;
+  amp* stage = nullptr;
+  uint64_t stage_chunk = 0;  // amps per (peer, buffer) slot
+  int stage_peers = 0;
+  cudaEvent_t ev_group[2] = {nullptr, nullptr};
+  cudaEvent_t ev_copy[2] = {nullptr, nullptr};
+  double* d_small = nullptr;  // 256 doubles
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;
+};
+
+DistState* st(qcsim_sv* h) { return static_cast<DistState*>(h->dist); }
+
+int log2i(int w) {
+  int l = 0;
+  while ((1 << l) < w) ++l;
+  return l;
+}
+
+}  // namespace
+
+int dist_unique_id(void* out) {
+  static_assert(sizeof(ncclUniqueId) == 128, "the ABI passes the NCCL id as 128 bytes");
+  if (!out) return fail(QCSIM_ERR_BAD_ARG, "null output");
+  ncclUniqueId id;
+  NCCL_TRY(ncclGetUniqueId(&id));
+  std::memcpy(out, &id, sizeof id);
+  return QCSIM_OK;
+}
 
 int engine_nccl_unique_id(void* out) { return dist_unique_id(out); }
+
+int dist_init(qcsim_sv* h, const void* nccl_id) {
+  if (!nccl_id) return fail(QCSIM_ERR_BAD_ARG, "sharded register needs the NCCL unique id");
+  if (h->n_local < 3) return fail(QCSIM_ERR_BAD_ARG, "a sharded register needs at least 3 local qubits per rank");
+  DistState* d = new DistState();
+  h->dist = d;
+  d->layout.reset(h->n, h->n_local);
+  ncclUniqueId id;
+  std::memcpy(&id, nccl_id, sizeof id);
+  NCCL_TRY(ncclCommInitRank(&d->comm, h->world, id, h->rank));
+  h->nccl_comm = d->comm;
+  CUDA_TRY(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    CUDA_TRY(cudaEventCreateWithFlags(&d->ev_group[i], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&d->ev_copy[i], cudaEventDisableTiming));
+  }
+  CUDA_TRY(cudaMalloc(&d->d_small, 256 * sizeof(double)));
+  return QCSIM_OK;
+}
+
+void dist_shutdown(qcsim_sv* h) {
+  DistState* d = st(h);
+  if (!d) return;
+  for (auto& p : d->timed) {
+    cudaEventDestroy(p.first);
+    cudaEventDestroy(p.second);
+  }
+  if (d->copy_stream) {
+    cudaStreamSynchronize(d->copy_stream);
+    cudaStreamDestroy(d->copy_stream);
+  }
+  for (int i = 0; i < 2; ++i) {
+    if (d->ev_group[i]) cudaEventDestroy(d->ev_group[i]);
+    if (d->ev_copy[i]) cudaEventDestroy(d->ev_copy[i]);
+  }
+  cudaFree(d->stage);
+  cudaFree(d->d_small);
+  if (d->comm) ncclCommDestroy(d->comm);
+  delete d;
+  h->dist = nullptr;
+  h->nccl_comm = nullptr;
+}
+
+void dist_reset_layout(qcsim_sv* h) {
+  if (st(h)) st(h)->layout.reset(h->n, h->n_local);
+}
+
+int dist_buffers_changed(qcsim_sv*) { return QCSIM_OK; }
+
+void dist_map_mask(qcsim_sv* h, uint64_t mask, uint64_t want, uint64_t* pmask, uint64_t* pwant) {
+  const DistLayout& L = st(h)->layout;
+  uint64_t pm = 0, pw = 0;
+  for (int q = 0; q < h->n; ++q) {
+    if ((mask >> q) & 1ULL) pm |= 1ULL << L.phys_of[q];
+    if ((want >> q) & 1ULL) pw |= 1ULL << L.phys_of[q];
+  }
+  *pmask = pm;
+  *pwant = pw;
+}
+
+// sum over ranks of `count` host doubles (count <= 256)
+int dist_allreduce_host(qcsim_sv* h, double* vals, int count) {
+  DistState* d = st(h);
+  if (count > 256) return fail(QCSIM_ERR_BAD_ARG, "internal: allreduce too large");
+  CUDA_TRY(cudaMemcpyAsync(d->d_small, vals, count * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  NCCL_TRY(ncclAllReduce(d->d_small, d->d_small, count, ncclDouble, ncclSum, d->comm, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(vals, d->d_small, count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return QCSIM_OK;
+}
+
+// every rank contributes `per` doubles; all[r * per + i] afterwards (exact: zeros elsewhere)
+static int allgather_host(qcsim_sv* h, const double* mine, int per, double* all) {
+  double buf[256];
+  const int total = per * h->world;
+  if (total > 256) return fail(QCSIM_ERR_BAD_ARG, "internal: allgather too large");
+  for (int i = 0; i < total; ++i) buf[i] = 0.0;
+  for (int i = 0; i < per; ++i) buf[h->rank * per + i] = mine[i];
+  QCSIM_TRY(dist_allreduce_host(h, buf, total));
+  for (int i = 0; i < total; ++i) all[i] = buf[i];
+  return QCSIM_OK;
+}
+
+// ---- exchange: swap physical global positions gpos[j] with the top-k local positions -------------
+
+static int ensure_stage(qcsim_sv* h, uint64_t chunk, int peers) {
+  DistState* d = st(h);
+  if (d->stage && d->stage_chunk >= chunk && d->stage_peers >= peers) return QCSIM_OK;
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  CUDA_TRY(cudaStreamSynchronize(d->copy_stream));
+  cudaFree(d->stage);
+  d->stage = nullptr;
+  const int all_peers = h->world - 1;
+  CUDA_TRY(cudaMalloc(&d->stage, sizeof(amp) * chunk * 2 * all_peers));
+  d->stage_chunk = chunk;
+  d->stage_peers = all_peers;
+  return QCSIM_OK;
+}
+
+static int do_exchange(qcsim_sv* h, const DistStep& ex) {
+  DistState* d = st(h);
+  const int k = ex.k, nl = h->n_local;
+  if (k < 1 || k > 3) return fail(QCSIM_ERR_BAD_ARG, "internal: bad exchange width");
+  const uint64_t blk = h->dim_local >> k;  // amps per sub-block
+  const uint64_t chunk = std::min<uint64_t>(blk, kStageChunkAmps);
+  const int n_sub = 1 << k;
+  QCSIM_TRY(ensure_stage(h, chunk, n_sub - 1));
+  int a = 0;  // my value of the swapped global bits
+  for (int j = 0; j < k; ++j) a |= ((h->rank >> (ex.gpos[j] - nl)) & 1) << j;
+  auto peer_of = [&](int t) {
+    int p = h->rank;
+    for (int j = 0; j < k; ++j) {
+      const int bit = 1 << (ex.gpos[j] - nl);
+      p = ((t >> j) & 1) ? (p | bit) : (p & ~bit);
+    }
+    return p;
+  };
+  auto slot = [&](int buf, int t) { return d->stage + ((uint64_t)(buf * (n_sub - 1) + (t < a ? t : t - 1))) * d->stage_chunk; };
+
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  CUDA_TRY(cudaEventRecord(e0, h->stream));
+  const uint64_t n_chunks = (blk + chunk - 1) / chunk;
+  bool copied[2] = {false, false};
+  for (uint64_t c = 0; c < n_chunks; ++c) {
+    const int buf = (int)(c & 1);
+    const uint64_t off = c * chunk;
+    const uint64_t cnt = std::min<uint64_t>(chunk, blk - off);
+    if (copied[buf]) CUDA_TRY(cudaStreamWaitEvent(h->stream, d->ev_copy[buf], 0));  // staging slot drained
+    NCCL_TRY(ncclGroupStart());
+    for (int t = 0; t < n_sub; ++t) {
+      if (t == a) continue;
+      const int peer = peer_of(t);
+      NCCL_TRY(ncclSend(h->psi + (uint64_t)t * blk + off, cnt * 2, ncclDouble, peer, d->comm, h->stream));
+      NCCL_TRY(ncclRecv(slot(buf, t), cnt * 2, ncclDouble, peer, d->comm, h->stream));
+    }
+    NCCL_TRY(ncclGroupEnd());
+    CUDA_TRY(cudaEventRecord(d->ev_group[buf], h->stream));
+    CUDA_TRY(cudaStreamWaitEvent(d->copy_stream, d->ev_group[buf], 0));
+    for (int t = 0; t < n_sub; ++t) {
+      if (t == a) continue;
+      CUDA_TRY(cudaMemcpyAsync(h->psi + (uint64_t)t * blk + off, slot(buf, t), cnt * sizeof(amp), cudaMemcpyDeviceToDevice,
+                               d->copy_stream));
+    }
+    CUDA_TRY(cudaEventRecord(d->ev_copy[buf], d->copy_stream));
+    copied[buf] = true;
+  }
+  for (int b = 0; b < 2; ++b)
+    if (copied[b]) CUDA_TRY(cudaStreamWaitEvent(h->stream, d->ev_copy[b], 0));
+  CUDA_TRY(cudaEventRecord(e1, h->stream));
+  d->timed.push_back({e0, e1});
+  h->stats.exchange_calls += 1;
+  h->stats.exchange_bytes += (uint64_t)(n_sub - 1) * blk * sizeof(amp);
+  return QCSIM_OK;
+}
+
+static int run_steps(qcsim_sv* h, const std::vector<DistStep>& steps) {
+  for (const DistStep& s : steps) {
+    if (s.exchange) QCSIM_TRY(do_exchange(h, s));
+    else QCSIM_TRY(fusion_execute_local(h, s.ops));
+  }
+  return QCSIM_OK;
+}
+
+int dist_execute(qcsim_sv* h, const std::vector<Op>& ops) {
+  DistState* d = st(h);
+  return run_steps(h, dist_plan(d->layout, ops, h->rank));
+}
+
+int dist_apply(qcsim_sv* h, const Op& op) {
+  std::vector<Op> one(1, op);
+  return dist_execute(h, one);
+}
+
+int dist_canonicalize(qcsim_sv* h) {
+  DistState* d = st(h);
+  if (d->layout.is_identity()) return QCSIM_OK;
+  return run_steps(h, dist_plan_canonicalize(d->layout));
+}
+
+void dist_collect_stats(qcsim_sv* h) {
+  DistState* d = st(h);
+  if (!d) return;
+  for (auto& p : d->timed) {
+    float ms = 0;
+    if (cudaEventSynchronize(p.second) == cudaSuccess && cudaEventElapsedTime(&ms, p.first, p.second) == cudaSuccess)
+      h->stats.exchange_ms += ms;
+    cudaEventDestroy(p.first);
+    cudaEventDestroy(p.second);
+  }
+  d->timed.clear();
+}
+
+// ---- measurement scan over all ranks (layout is canonical here) -----------------------------------
+
+int dist_pick_state(qcsim_sv* h, double prob, uint64_t fallback, uint64_t* outcome) {
+  const int W = h->world;
+  const int g = (int)std::min<uint64_t>(h->n_chunks, (uint64_t)kNumSMs * 8);
+  ScanResult* res = (ScanResult*)h->h_pinned;
+  // 1. exact mass of every rank's slice
+  k_chunk_sums<<<g, kThreads, 0, h->stream>>>(h->psi, h->dim_local, h->n_chunks, h->d_chunk_sums);
+  k_find_chunk<<<1, 1024, 0, h->stream>>>(h->d_chunk_sums, h->n_chunks, dd_make(0, 0), 2.0, h->d_scan);  // prob 2: totals only
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(res, h->d_scan, sizeof(ScanResult), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  h->stats.kernel_launches += 2;
+  h->stats.state_passes += 1;
+  h->stats.bytes_moved += 16ULL * h->dim_local;
+  double mine[2] = {res->total.hi, res->total.lo};
+  double all[256];
+  QCSIM_TRY(allgather_host(h, mine, 2, all));
+  dd offset = dd_make(0, 0);
+  for (int r = 0; r < h->rank; ++r) offset = dd_add(offset, dd_make(all[2 * r], all[2 * r + 1]));
+  // 2. locate inside the slice, with the mass of the lower ranks as the starting prefix
+  k_find_chunk<<<1, 1024, 0, h->stream>>>(h->d_chunk_sums, h->n_chunks, offset, prob, h->d_scan);
+  k_find_in_chunk<<<1, kThreads, 0, h->stream>>>(h->psi, h->dim_local, prob, h->d_scan);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(res, h->d_scan, sizeof(ScanResult), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  h->stats.kernel_launches += 2;
+  double cand[2] = {res->found ? 1.0 : 0.0, res->found ? (double)(((uint64_t)h->rank << h->n_local) | res->index) : 0.0};
+  QCSIM_TRY(allgather_host(h, cand, 2, all));
+  uint64_t s = fallback;
+  for (int r = 0; r < W; ++r)
+    if (all[2 * r] != 0.0) {
+      s = (uint64_t)all[2 * r + 1];
+      break;
+    }
+  if (h->strict_measure) {
+    // replay the reference's sequential fp64 sum rank by rank (QubitRegister.h:172-190)
+    unsigned long long* d_idx = (unsigned long long*)(h->d_scalars + 8);
+    double acc = 0.0;
+    s = fallback;
+    bool done = false;
+    for (int r = 0; r < W && !done; ++r) {
+      double out[2] = {0.0, 0.0};  // (found index + 1 or 0, running sum)
+      if (r == h->rank) {
+        k_sequential_scan<<<1, kThreads, 0, h->stream>>>(h->psi, h->dim_local, acc, prob, d_idx, h->d_scalars + 9);
+        CUDA_TRY(cudaGetLastError());
+        h->stats.kernel_launches += 1;
+        unsigned long long* stage = (unsigned long long*)((char*)h->h_pinned + 1024);
+        double* stage_acc = (double*)((char*)h->h_pinned + 1040);
+        CUDA_TRY(cudaMemcpyAsync(stage, d_idx, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaMemcpyAsync(stage_acc, h->d_scalars + 9, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        out[0] = (*stage == ~0ULL) ? 0.0 : (double)(*stage + 1);
+        out[1] = *stage_acc;
+      }
+      QCSIM_TRY(dist_allreduce_host(h, out, 2));  // only rank r contributed
+      if (out[0] != 0.0) {
+        s = ((uint64_t)r << h->n_local) | ((uint64_t)out[0] - 1);
+        done = true;
+      }
+      acc = out[1];
+    }
+  }
+  *outcome = s;
+  return QCSIM_OK;
+}
 
 }  // namespace qcsim

@@ -16,5 +16,6 @@ int dist_allreduce_host(qcsim_sv* h, double* vals, int count);
 int dist_apply(qcsim_sv* h, const Op& op);
 int dist_canonicalize(qcsim_sv* h);
 int dist_pick_state(qcsim_sv* h, double prob, uint64_t fallback, uint64_t* outcome);
+void dist_collect_stats(qcsim_sv* h);  // resolves the CUDA-event timings of finished exchanges into stats.exchange_ms
 
 }  // namespace qcsim

@@ -1,0 +1,318 @@
+// dist_plan.h -- planning for sharded registers.  Pure host code (no CUDA, no NCCL): unit-tested
+// on the CPU with simulated shards (tests/test_dist_plan.py) before it ever meets a GPU.
+//
+// The state of n qubits is split over world = 2^g ranks.  PHYSICAL bit positions
+// [0, n_local) address an amplitude inside a rank's slice, positions [n_local, n) are the bits of
+// the rank number.  A DistLayout maps the LOGICAL qubits of the circuit onto physical positions;
+// it starts as the identity (rank = top g qubits) and changes when
+//   * a SWAP gate is applied: pure relabelling, no data moves;
+//   * a gate needs non-diagonal access to a qubit that currently sits on a global position: the
+//     planner emits an EXCHANGE step that swaps k global positions with the top k local positions
+//     (an all-to-all among the 2^k ranks that differ in those bits; contiguous 2^(n_local-k)
+//     blocks, so no pack/unpack kernels), preceded by local SWAP passes that park the k local
+//     qubits whose next non-diagonal use is farthest away on those top positions.
+// Everything else is shard-local: controls on global positions are decided per rank (run or
+// skip), diagonal selectors on global positions are folded into the table.  The layout is only
+// brought back to the identity (dist_plan_canonicalize) when the caller looks at amplitudes.
+#pragma once
+
+#include <algorithm>
+#include <cstdint>
+#include <vector>
+
+#include "classify.h"
+#include "planner.h"
+
+namespace qcsim {
+
+struct DistLayout {
+  int n = 0, n_local = 0;
+  int phys_of[64];  // logical qubit -> physical position
+  int log_of[64];   // physical position -> logical qubit
+
+  void reset(int n_, int n_local_) {
+    n = n_;
+    n_local = n_local_;
+    for (int q = 0; q < 64; ++q) phys_of[q] = log_of[q] = q;
+  }
+  bool is_identity() const {
+    for (int q = 0; q < n; ++q)
+      if (phys_of[q] != q) return false;
+    return true;
+  }
+  void swap_logical(int a, int b) {
+    std::swap(phys_of[a], phys_of[b]);
+    log_of[phys_of[a]] = a;
+    log_of[phys_of[b]] = b;
+  }
+  void swap_physical(int x, int y) { swap_logical(log_of[x], log_of[y]); }
+  bool is_global(int logical) const { return phys_of[logical] >= n_local; }
+};
+
+struct DistStep {
+  bool exchange = false;
+  std::vector<Op> ops;  // !exchange: ops on physical LOCAL positions, folded for this rank
+  int k = 0;            // exchange: physical position gpos[j] <-> lpos[j] = n_local - k + j
+  int gpos[3] = {0, 0, 0};
+  int lpos[3] = {0, 0, 0};
+};
+
+namespace detail {
+
+inline bool is_plain_swap(const Op& op) {
+  return op.kind == OP_PAIR && op.n_tgt == 2 && op.n_ctrl == 0 && op.m[0] == cplx(0, 0) && op.m[3] == cplx(0, 0) &&
+         op.m[1] == cplx(1, 0) && op.m[2] == cplx(1, 0);
+}
+
+inline Op physical_swap_op(int x, int y) {
+  Op op;
+  std::memset(&op, 0, sizeof(op));
+  op.kind = OP_PAIR;
+  op.n_tgt = 2;
+  op.tgt[0] = x;
+  op.tgt[1] = y;
+  op.m[1] = op.m[2] = cplx(1, 0);
+  return op;
+}
+
+}  // namespace detail
+
+// Logical op -> op on physical local positions for `rank`.  Returns false when the op does
+// nothing on this rank (a control on a global position is 0 here, or the folded table is 1).
+// Precondition: every non-diagonal target is on a local position.
+inline bool fold_to_physical(const Op& in, const DistLayout& L, int rank, Op* out) {
+  Op op = in;
+  const int nl = L.n_local;
+  auto rank_bit = [&](int p) { return (rank >> (p - nl)) & 1; };
+  int nc = 0;
+  for (int i = 0; i < in.n_ctrl; ++i) {
+    const int p = L.phys_of[in.ctrl[i]];
+    if (p >= nl) {
+      if (!rank_bit(p)) return false;
+    } else {
+      op.ctrl[nc++] = p;
+    }
+  }
+  op.n_ctrl = nc;
+  for (int i = nc; i < 3; ++i) op.ctrl[i] = 0;
+  if (in.kind == OP_DIAG) {
+    int nt = 0;
+    int keep_pos[3];
+    int fixed_mask = 0, fixed_val = 0;
+    for (int k = 0; k < in.n_tgt; ++k) {
+      const int p = L.phys_of[in.tgt[k]];
+      if (p >= nl) {
+        fixed_mask |= 1 << k;
+        if (rank_bit(p)) fixed_val |= 1 << k;
+      } else {
+        keep_pos[nt] = k;
+        op.tgt[nt++] = p;
+      }
+    }
+    cplx t[8];
+    for (int j = 0; j < (1 << nt); ++j) {
+      int idx = fixed_val;
+      for (int b = 0; b < nt; ++b)
+        if ((j >> b) & 1) idx |= 1 << keep_pos[b];
+      t[j] = in.m[idx];
+    }
+    (void)fixed_mask;
+    for (int j = 0; j < 8; ++j) op.m[j] = j < (1 << nt) ? t[j] : cplx(0, 0);
+    op.n_tgt = nt;
+    for (int i = nt; i < 3; ++i) op.tgt[i] = 0;
+    bool all_one = true;
+    for (int j = 0; j < (1 << nt); ++j) all_one = all_one && detail::is_one(op.m[j]);
+    if (all_one) return false;
+  } else {
+    for (int k = 0; k < in.n_tgt; ++k) op.tgt[k] = L.phys_of[in.tgt[k]];
+  }
+  *out = op;
+  return true;
+}
+
+// Plans `ops_in` (logical qubits, program order) for `rank`.  The exchange steps and the layout
+// evolution depend only on the op list, never on the rank, so all ranks stay in lock step.
+inline std::vector<DistStep> dist_plan(DistLayout& L, const std::vector<Op>& ops_in, int rank) {
+  using namespace detail;
+  const int nl = L.n_local, n = L.n;
+  const int g = n - nl;
+  std::vector<DistStep> steps;
+
+  // 1. SWAP gates become relabellings: rewrite the ops that follow onto the pre-swap names
+  int sigma[64];
+  for (int q = 0; q < 64; ++q) sigma[q] = q;
+  std::vector<Op> ops;
+  ops.reserve(ops_in.size());
+  for (const Op& o : ops_in) {
+    if (o.kind == OP_NOP) continue;
+    if (is_plain_swap(o)) {
+      std::swap(sigma[o.tgt[0]], sigma[o.tgt[1]]);
+      continue;
+    }
+    Op r = o;
+    for (int i = 0; i < r.n_ctrl; ++i) r.ctrl[i] = sigma[o.ctrl[i]];
+    for (int i = 0; i < r.n_tgt; ++i) r.tgt[i] = sigma[o.tgt[i]];
+    ops.push_back(r);
+  }
+  const int N = (int)ops.size();
+
+  // 2. next non-diagonal use of every logical qubit
+  std::vector<std::vector<int>> uses(n);
+  std::vector<uint64_t> nd(N);
+  for (int i = 0; i < N; ++i) {
+    nd[i] = masks_of(ops[i]).nd;
+    for (int q = 0; q < n; ++q)
+      if ((nd[i] >> q) & 1ULL) uses[q].push_back(i);
+  }
+  std::vector<size_t> cursor(n, 0);
+  const int kNever = 1 << 30;
+  auto next_use = [&](int q, int i) {
+    size_t& c = cursor[q];
+    while (c < uses[q].size() && uses[q][c] < i) ++c;
+    return c < uses[q].size() ? uses[q][c] : kNever;
+  };
+
+  DistStep cur;
+  auto flush_local = [&]() {
+    if (!cur.ops.empty()) steps.push_back(cur);
+    cur = DistStep();
+  };
+
+  for (int i = 0; i < N; ++i) {
+    const Op& op = ops[i];
+    bool needs_global = false;
+    for (int q = 0; q < n; ++q)
+      if (((nd[i] >> q) & 1ULL) && L.is_global(q)) needs_global = true;
+    if (needs_global) {
+      // incoming: global-resident logical qubits by next use; outgoing: local ones, farthest first
+      std::vector<std::pair<int, int>> incoming, outgoing;  // (next use, logical)
+      for (int q = 0; q < n; ++q) {
+        const int nu = next_use(q, i);
+        if (L.is_global(q)) incoming.push_back({nu, q});
+        else if (!((nd[i] >> q) & 1ULL)) outgoing.push_back({nu, q});
+      }
+      std::sort(incoming.begin(), incoming.end());
+      // farthest next use first; ties: prefer the qubit already highest up (fewer local swaps)
+      std::sort(outgoing.begin(), outgoing.end(), [&](const std::pair<int, int>& a, const std::pair<int, int>& b) {
+        if (a.first != b.first) return a.first > b.first;
+        return L.phys_of[a.second] > L.phys_of[b.second];
+      });
+      int k = 0;
+      std::vector<int> in_q, out_q;
+      for (size_t j = 0; j < incoming.size() && j < outgoing.size() && (int)j < g; ++j) {
+        const bool mandatory = incoming[j].first == i;
+        if (!mandatory && !(incoming[j].first < outgoing[j].first)) break;
+        in_q.push_back(incoming[j].second);
+        out_q.push_back(outgoing[j].second);
+        ++k;
+      }
+      // park the outgoing qubits on the top k local positions
+      for (int j = 0; j < k; ++j) {
+        const int slot = nl - k + j;
+        const int occupant = L.log_of[slot];
+        if (std::find(out_q.begin(), out_q.end(), occupant) != out_q.end()) continue;
+        int mover = -1;
+        for (int v : out_q)
+          if (L.phys_of[v] < nl - k) {
+            mover = v;
+            break;
+          }
+        cur.ops.push_back(physical_swap_op(L.phys_of[mover], slot));
+        L.swap_physical(L.phys_of[mover], slot);
+      }
+      flush_local();
+      DistStep ex;
+      ex.exchange = true;
+      ex.k = k;
+      for (int j = 0; j < k; ++j) {
+        ex.gpos[j] = L.phys_of[in_q[j]];
+        ex.lpos[j] = nl - k + j;
+      }
+      steps.push_back(ex);
+      for (int j = 0; j < k; ++j) L.swap_physical(ex.gpos[j], ex.lpos[j]);
+    }
+    Op phys;
+    if (fold_to_physical(op, L, rank, &phys)) cur.ops.push_back(phys);
+  }
+  flush_local();
+
+  // 3. account for the relabellings: logical q now names the data that was called sigma[q]
+  int new_phys[64];
+  for (int q = 0; q < n; ++q) new_phys[q] = L.phys_of[sigma[q]];
+  for (int q = 0; q < n; ++q) {
+    L.phys_of[q] = new_phys[q];
+    L.log_of[new_phys[q]] = q;
+  }
+  return steps;
+}
+
+// Steps that bring the layout back to the identity (<= 2 exchanges + local SWAP passes).
+inline std::vector<DistStep> dist_plan_canonicalize(DistLayout& L) {
+  using namespace detail;
+  const int nl = L.n_local, n = L.n;
+  std::vector<DistStep> steps;
+  auto wrong_globals = [&]() {
+    std::vector<int> w;
+    for (int p = nl; p < n; ++p)
+      if (L.log_of[p] != p) w.push_back(p);
+    return w;
+  };
+  auto do_exchange = [&](const std::vector<int>& gp) {
+    DistStep ex;
+    ex.exchange = true;
+    ex.k = (int)gp.size();
+    for (int j = 0; j < ex.k; ++j) {
+      ex.gpos[j] = gp[j];
+      ex.lpos[j] = nl - ex.k + j;
+    }
+    steps.push_back(ex);
+    for (int j = 0; j < ex.k; ++j) L.swap_physical(ex.gpos[j], ex.lpos[j]);
+  };
+  std::vector<int> w = wrong_globals();
+  if (!w.empty()) {
+    // phase A: qubits that belong on a global position but sit on ANOTHER global position come
+    // down first, traded against local qubits that have no business up there
+    std::vector<int> stray;
+    for (int p : w)
+      if (L.log_of[p] >= nl) stray.push_back(p);
+    if (!stray.empty()) {
+      const int a = (int)stray.size();
+      DistStep park;
+      for (int j = 0; j < a; ++j) {
+        const int slot = nl - a + j;
+        if (L.log_of[slot] < nl) continue;  // already a plain local qubit
+        int donor = -1;
+        for (int x = 0; x < nl - a; ++x)
+          if (L.log_of[x] < nl) {
+            donor = x;
+            break;
+          }
+        park.ops.push_back(physical_swap_op(donor, slot));
+        L.swap_physical(donor, slot);
+      }
+      if (!park.ops.empty()) steps.push_back(park);
+      do_exchange(stray);
+    }
+    w = wrong_globals();
+    const int k = (int)w.size();
+    DistStep loc;
+    for (int j = 0; j < k; ++j) {
+      const int slot = nl - k + j;
+      if (L.log_of[slot] == w[j]) continue;
+      loc.ops.push_back(physical_swap_op(L.phys_of[w[j]], slot));
+      L.swap_physical(L.phys_of[w[j]], slot);
+    }
+    if (!loc.ops.empty()) steps.push_back(loc);
+    if (k) do_exchange(w);
+  }
+  DistStep loc;
+  for (int p = 0; p < nl; ++p) {
+    if (L.log_of[p] == p) continue;
+    loc.ops.push_back(physical_swap_op(p, L.phys_of[p]));
+    L.swap_physical(p, L.phys_of[p]);
+  }
+  if (!loc.ops.empty()) steps.push_back(loc);
+  return steps;
+}
+
+}  // namespace qcsim

@@ -68,7 +68,7 @@ __device__ __forceinline__ dd block_sum_dd(dd v) {
 // sum of |a|^2 over local indices i with ((base + i) & mask) == want -> partials[blockIdx.x]
 // mask == 0: squared norm; mask = bit, want = bit: GetQubitProbability (Calculator :1088-1122);
 // mask = measured part: the collapse norm of Measure (:980-987, 1151-1158).
-__global__ void __launch_bounds__(kThreads)
+static __global__ void __launch_bounds__(kThreads)
 k_masked_norm2(const amp* __restrict__ psi, uint64_t n, uint64_t base, uint64_t mask, uint64_t want,
                double* __restrict__ partials) {
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -88,7 +88,7 @@ k_masked_norm2(const amp* __restrict__ psi, uint64_t n, uint64_t base, uint64_t 
 }
 
 // conj(a) . b partials (stateFidelity / ExpectationValue, QubitRegister.h:527-534, 646-660)
-__global__ void __launch_bounds__(kThreads)
+static __global__ void __launch_bounds__(kThreads)
 k_inner_product(const amp* __restrict__ a, const amp* __restrict__ b, uint64_t n, double* __restrict__ partials) {
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   double re = 0, im = 0;
@@ -106,7 +106,7 @@ k_inner_product(const amp* __restrict__ a, const amp* __restrict__ b, uint64_t n
 }
 
 // deterministic final reduction of `count` partials (x `width` interleaved components)
-__global__ void __launch_bounds__(kThreads) k_final_sum(const double* __restrict__ partials, int count, int width,
+static __global__ void __launch_bounds__(kThreads) k_final_sum(const double* __restrict__ partials, int count, int width,
                                                         double* __restrict__ out) {
   for (int c = 0; c < width; ++c) {
     double acc = 0;
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(kThreads) k_final_sum(const double* __restrict
 // ---- measurement scan --------------------------------------------------------------------------
 
 // chunk c = amplitudes [c*kChunk, (c+1)*kChunk) (clipped to n): error-free probability mass
-__global__ void __launch_bounds__(kThreads)
+static __global__ void __launch_bounds__(kThreads)
 k_chunk_sums(const amp* __restrict__ psi, uint64_t n, uint64_t n_chunks, dd* __restrict__ sums) {
   for (uint64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
     const uint64_t lo = c << kChunkLog2;
@@ -141,7 +141,7 @@ struct ScanResult {
 };
 
 // Single block.  `offset` = exact mass owned by lower ranks (0 on one GPU).
-__global__ void __launch_bounds__(1024)
+static __global__ void __launch_bounds__(1024)
 k_find_chunk(const dd* __restrict__ sums, uint64_t n_chunks, dd offset, double prob, ScanResult* __restrict__ res) {
   __shared__ dd tot[1024];
   __shared__ unsigned long long first_chunk;
@@ -192,7 +192,7 @@ k_find_chunk(const dd* __restrict__ sums, uint64_t n_chunks, dd offset, double p
 }
 
 // Single block of kThreads: locate the outcome inside res->chunk.
-__global__ void __launch_bounds__(kThreads)
+static __global__ void __launch_bounds__(kThreads)
 k_find_in_chunk(const amp* __restrict__ psi, uint64_t n, double prob, ScanResult* __restrict__ res) {
   if (!res->found) return;
   constexpr int PER = (int)(kChunk / kThreads);
@@ -248,7 +248,7 @@ k_find_in_chunk(const amp* __restrict__ psi, uint64_t n, double prob, ScanResult
 // local indices [0, upto]: acc_{i} = fl(acc_{i-1} + p_i), starting from `start`.  One block;
 // the adds are one dependent chain on a single thread, the loads are cooperative.
 // Writes the first index with prob <= acc (or ~0) and the final acc.
-__global__ void __launch_bounds__(kThreads)
+static __global__ void __launch_bounds__(kThreads)
 k_sequential_scan(const amp* __restrict__ psi, uint64_t n, double start, double prob, unsigned long long* __restrict__ out_idx,
                   double* __restrict__ out_acc) {
   __shared__ double buf[2][kThreads * 8];

@@ -54,3 +54,48 @@ int hl_plan(const qcsim_gate* gates, int count, int n_local, int K, int L, int* 
   return (int)steps.size();
 }
 }
+
+// ---- sharded planning (dist_plan.h) -----------------------------------------------------------
+#include "../../qcsim_b200/csrc/dist_plan.h"
+
+extern "C" {
+
+// Plans `count` gates for `rank` from the layout phys_of[0..n) (updated in place).  Steps are
+// written flat: step_kind (0 local, 1 exchange), step_nops / ops_out for local steps, ex_k /
+// ex_g / ex_l (3 ints per step) for exchanges.  canonicalize != 0: plan the return to the identity
+// layout instead (gates ignored).  Returns the number of steps, or -1 if a buffer is too small.
+int hl_dist_plan(const qcsim_gate* gates, int count, int n, int n_local, int rank, int* phys_of, int canonicalize,
+                 int max_steps, int max_ops, int* step_kind, int* step_nops, hl_op* ops_out, int* ex_k, int* ex_g, int* ex_l) {
+  DistLayout L;
+  L.reset(n, n_local);
+  for (int q = 0; q < n; ++q) {
+    L.phys_of[q] = phys_of[q];
+    L.log_of[phys_of[q]] = q;
+  }
+  std::vector<DistStep> steps;
+  if (canonicalize) {
+    steps = dist_plan_canonicalize(L);
+  } else {
+    std::vector<Op> ops;
+    for (int i = 0; i < count; ++i) ops.push_back(classify(gates[i].nq, gates[i].m, gates[i].flags, gates[i].q, gates[i].c1, gates[i].c2));
+    steps = dist_plan(L, ops, rank);
+  }
+  if ((int)steps.size() > max_steps) return -1;
+  int o = 0;
+  for (size_t s = 0; s < steps.size(); ++s) {
+    step_kind[s] = steps[s].exchange ? 1 : 0;
+    step_nops[s] = (int)steps[s].ops.size();
+    ex_k[s] = steps[s].k;
+    for (int j = 0; j < 3; ++j) {
+      ex_g[3 * s + j] = steps[s].gpos[j];
+      ex_l[3 * s + j] = steps[s].lpos[j];
+    }
+    for (const Op& op : steps[s].ops) {
+      if (o >= max_ops) return -1;
+      export_op(op, &ops_out[o++]);
+    }
+  }
+  for (int q = 0; q < n; ++q) phys_of[q] = L.phys_of[q];
+  return (int)steps.size();
+}
+}

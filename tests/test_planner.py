@@ -24,7 +24,7 @@ class HlOp(C.Structure):
 @pytest.fixture(scope="module")
 def hl():
     src = os.path.join(HERE, "cpp", "hostlogic.cpp")
-    deps = [src] + [os.path.join(HERE, "..", "qcsim_b200", "csrc", f) for f in ("classify.h", "planner.h")]
+    deps = [src] + [os.path.join(HERE, "..", "qcsim_b200", "csrc", f) for f in ("classify.h", "planner.h", "dist_plan.h")]
     if not os.path.exists(SO) or any(os.path.getmtime(SO) < os.path.getmtime(d) for d in deps):
         subprocess.run(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", src, "-o", SO], check=True)
     lib = C.CDLL(SO)
