@@ -329,6 +329,7 @@ int qcsim_sv_get_stats(const qcsim_sv* h, qcsim_stats* out) {
 
 int qcsim_sv_reset_stats(qcsim_sv* h) {
   if (!h) return fail(QCSIM_ERR_BAD_ARG, "null register handle");
+  if (h->world > 1) dist_collect_stats(h);  // drop the timings of exchanges that finished before the reset
   std::memset(&h->stats, 0, sizeof(h->stats));
   return QCSIM_OK;
 }

@@ -13,6 +13,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "dist.h"
@@ -30,7 +31,14 @@ namespace qcsim {
 
 namespace {
 
-constexpr uint64_t kStageChunkAmps = 1ULL << 22;  // 64 MiB per peer per buffer
+static uint64_t stage_chunk_amps() {  // amps per peer per buffer (default 2^22 = 64 MiB)
+  static const uint64_t v = [] {
+    const char* s = std::getenv("QCSIM_EXCHANGE_CHUNK_LOG2");
+    const int l = s ? std::atoi(s) : 22;
+    return 1ULL << std::max(4, std::min(l, 32));
+  }();
+  return v;
+}
 
 struct DistState {
   ncclComm_t comm = nullptr;
@@ -43,6 +51,9 @@ struct DistState {
   cudaEvent_t ev_copy[2] = {nullptr, nullptr};
   double* d_small = nullptr;  // 256 doubles
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;
+  // peer-memory path: every rank's slice mapped into this process through CUDA IPC
+  bool p2p = false;
+  amp* peer_psi[64] = {};
 };
 
 DistState* st(qcsim_sv* h) { return static_cast<DistState*>(h->dist); }
@@ -54,6 +65,10 @@ int log2i(int w) {
 }
 
 }  // namespace
+
+static int setup_peers(qcsim_sv* h);
+static void close_peers(qcsim_sv* h);
+static int stream_barrier(qcsim_sv* h);
 
 int dist_unique_id(void* out) {
   static_assert(sizeof(ncclUniqueId) == 128, "the ABI passes the NCCL id as 128 bytes");
@@ -68,7 +83,7 @@ int engine_nccl_unique_id(void* out) { return dist_unique_id(out); }
 
 int dist_init(qcsim_sv* h, const void* nccl_id) {
   if (!nccl_id) return fail(QCSIM_ERR_BAD_ARG, "sharded register needs the NCCL unique id");
-  if (h->n_local < 3) return fail(QCSIM_ERR_BAD_ARG, "a sharded register needs at least 3 local qubits per rank");
+  if (h->n_local < 4) return fail(QCSIM_ERR_BAD_ARG, "a sharded register needs at least 4 local qubits per rank");
   DistState* d = new DistState();
   h->dist = d;
   d->layout.reset(h->n, h->n_local);
@@ -82,7 +97,8 @@ int dist_init(qcsim_sv* h, const void* nccl_id) {
     CUDA_TRY(cudaEventCreateWithFlags(&d->ev_copy[i], cudaEventDisableTiming));
   }
   CUDA_TRY(cudaMalloc(&d->d_small, 256 * sizeof(double)));
-  return QCSIM_OK;
+  CUDA_TRY(cudaMemset(d->d_small, 0, 256 * sizeof(double)));
+  return setup_peers(h);
 }
 
 void dist_shutdown(qcsim_sv* h) {
@@ -100,6 +116,11 @@ void dist_shutdown(qcsim_sv* h) {
     if (d->ev_group[i]) cudaEventDestroy(d->ev_group[i]);
     if (d->ev_copy[i]) cudaEventDestroy(d->ev_copy[i]);
   }
+  if (d->comm && d->p2p) {  // nobody may unmap a slice a peer is still swapping with
+    stream_barrier(h);
+    cudaStreamSynchronize(h->stream);
+  }
+  close_peers(h);
   cudaFree(d->stage);
   cudaFree(d->d_small);
   if (d->comm) ncclCommDestroy(d->comm);
@@ -112,7 +133,7 @@ void dist_reset_layout(qcsim_sv* h) {
   if (st(h)) st(h)->layout.reset(h->n, h->n_local);
 }
 
-int dist_buffers_changed(qcsim_sv*) { return QCSIM_OK; }
+int dist_buffers_changed(qcsim_sv* h) { return setup_peers(h); }
 
 void dist_map_mask(qcsim_sv* h, uint64_t mask, uint64_t want, uint64_t* pmask, uint64_t* pwant) {
   const DistLayout& L = st(h)->layout;
@@ -148,6 +169,110 @@ static int allgather_host(qcsim_sv* h, const double* mine, int per, double* all)
   return QCSIM_OK;
 }
 
+// ---- peer-memory exchange kernel --------------------------------------------------------------------
+// In-place swap of my block with the matching block of each peer, straight over NVLink: no staging
+// buffer, no second copy.  Of every pair of ranks, the lower one swaps the first half of the block
+// and the higher one the second half, so each direction of each link carries the same load
+// (half as remote stores issued here, half as remote loads issued by the peer).
+struct SwapArgs {
+  int n_peers;
+  amp* remote[7];        // peer's slice + offset of the block it trades with me
+  uint64_t mine_off[7];  // offset of my block for that peer
+  uint64_t first[7];     // my share of the block: [first, first + count)
+  uint64_t count[7];     // in units of amp2 (two amplitudes, 32 bytes)
+};
+
+__global__ void __launch_bounds__(256) k_exchange_swap(amp* __restrict__ mine, const __grid_constant__ SwapArgs A) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (int p = 0; p < A.n_peers; ++p) {
+    amp* m = mine + A.mine_off[p] + 2 * A.first[p];
+    amp* r = A.remote[p] + 2 * A.first[p];
+    const uint64_t n2 = A.count[p];
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n2; i += 4 * stride) {  // 4 x 32 B remote loads in flight per thread
+      amp2 x[4], y[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) y[u] = ld_amp2(r + 2 * (i + u * stride));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) x[u] = ld_amp2(m + 2 * (i + u * stride));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        st_amp2(m + 2 * (i + u * stride), y[u]);
+        st_amp2(r + 2 * (i + u * stride), x[u]);
+      }
+    }
+    for (; i < n2; i += stride) {
+      const amp2 y = ld_amp2(r + 2 * i), x = ld_amp2(m + 2 * i);
+      st_amp2(m + 2 * i, y);
+      st_amp2(r + 2 * i, x);
+    }
+  }
+}
+
+static void close_peers(qcsim_sv* h) {
+  DistState* d = st(h);
+  for (int r = 0; r < h->world; ++r) {
+    if (d->peer_psi[r] && r != h->rank) cudaIpcCloseMemHandle(d->peer_psi[r]);
+    d->peer_psi[r] = nullptr;
+  }
+  d->p2p = false;
+}
+
+// Collective: (re)map every rank's slice.  Falls back to the NCCL send/recv path if CUDA IPC is
+// not usable here (QCSIM_EXCHANGE=nccl forces that path).
+static int setup_peers(qcsim_sv* h) {
+  DistState* d = st(h);
+  close_peers(h);
+  const char* mode = std::getenv("QCSIM_EXCHANGE");
+  const bool want = !(mode && std::strcmp(mode, "nccl") == 0);
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  if (h->world * 8 + 8 > 256) return fail(QCSIM_ERR_BAD_ARG, "internal: too many ranks for the handle exchange");
+  cudaIpcMemHandle_t mine_h;
+  std::memset(&mine_h, 0, sizeof mine_h);
+  double ok = want ? 1.0 : 0.0;
+  if (want && cudaIpcGetMemHandle(&mine_h, h->psi) != cudaSuccess) {
+    cudaGetLastError();
+    ok = 0.0;
+  }
+  double* slot_mine = d->d_small + 8 * h->rank;  // 64 bytes per rank
+  CUDA_TRY(cudaMemcpyAsync(slot_mine, &mine_h, 64, cudaMemcpyHostToDevice, h->stream));
+  NCCL_TRY(ncclAllGather(slot_mine, d->d_small, 8, ncclDouble, d->comm, h->stream));
+  cudaIpcMemHandle_t all[64];
+  CUDA_TRY(cudaMemcpyAsync(all, d->d_small, 64 * h->world, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (ok != 0.0) {
+    for (int r = 0; r < h->world; ++r) {
+      if (r == h->rank) {
+        d->peer_psi[r] = h->psi;
+        continue;
+      }
+      void* ptr = nullptr;
+      if (cudaIpcOpenMemHandle(&ptr, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        ok = 0.0;
+        break;
+      }
+      d->peer_psi[r] = (amp*)ptr;
+    }
+  }
+  double agree = ok;  // every rank must take the same path
+  double buf[64];
+  for (int r = 0; r < h->world; ++r) buf[r] = 0.0;
+  buf[h->rank] = agree;
+  QCSIM_TRY(dist_allreduce_host(h, buf, h->world));
+  bool all_ok = true;
+  for (int r = 0; r < h->world; ++r) all_ok = all_ok && buf[r] != 0.0;
+  if (!all_ok) close_peers(h);
+  d->p2p = all_ok;
+  return QCSIM_OK;
+}
+
+static int stream_barrier(qcsim_sv* h) {  // stream-ordered barrier over all ranks
+  DistState* d = st(h);
+  NCCL_TRY(ncclAllReduce(d->d_small + 200, d->d_small + 200, 1, ncclDouble, ncclSum, d->comm, h->stream));
+  return QCSIM_OK;
+}
+
 // ---- exchange: swap physical global positions gpos[j] with the top-k local positions -------------
 
 static int ensure_stage(qcsim_sv* h, uint64_t chunk, int peers) {
@@ -169,9 +294,8 @@ static int do_exchange(qcsim_sv* h, const DistStep& ex) {
   const int k = ex.k, nl = h->n_local;
   if (k < 1 || k > 3) return fail(QCSIM_ERR_BAD_ARG, "internal: bad exchange width");
   const uint64_t blk = h->dim_local >> k;  // amps per sub-block
-  const uint64_t chunk = std::min<uint64_t>(blk, kStageChunkAmps);
+  const uint64_t chunk = std::min<uint64_t>(blk, stage_chunk_amps());
   const int n_sub = 1 << k;
-  QCSIM_TRY(ensure_stage(h, chunk, n_sub - 1));
   int a = 0;  // my value of the swapped global bits
   for (int j = 0; j < k; ++j) a |= ((h->rank >> (ex.gpos[j] - nl)) & 1) << j;
   auto peer_of = [&](int t) {
@@ -187,6 +311,37 @@ static int do_exchange(qcsim_sv* h, const DistStep& ex) {
   cudaEvent_t e0, e1;
   CUDA_TRY(cudaEventCreate(&e0));
   CUDA_TRY(cudaEventCreate(&e1));
+  if (d->p2p) {
+    SwapArgs A;
+    std::memset(&A, 0, sizeof A);
+    for (int t = 0; t < n_sub; ++t) {
+      if (t == a) continue;
+      const int peer = peer_of(t);
+      const int j = A.n_peers++;
+      A.remote[j] = d->peer_psi[peer] + (uint64_t)a * blk;  // the peer trades its block `a` for my block `t`
+      A.mine_off[j] = (uint64_t)t * blk;
+      const uint64_t pairs = blk / 2;  // amp2 units; blk is a power of two >= 2 here
+      if (pairs < 2) {
+        A.first[j] = 0;
+        A.count[j] = h->rank < peer ? pairs : 0;
+      } else {
+        A.first[j] = h->rank < peer ? 0 : pairs / 2;
+        A.count[j] = pairs / 2;
+      }
+    }
+    QCSIM_TRY(stream_barrier(h));  // every rank has finished writing its slice
+    CUDA_TRY(cudaEventRecord(e0, h->stream));
+    k_exchange_swap<<<kNumSMs * 8, 256, 0, h->stream>>>(h->psi, A);
+    CUDA_TRY(cudaGetLastError());
+    QCSIM_TRY(stream_barrier(h));  // every rank has finished swapping
+    CUDA_TRY(cudaEventRecord(e1, h->stream));
+    d->timed.push_back({e0, e1});
+    h->stats.kernel_launches += 1;
+    h->stats.exchange_calls += 1;
+    h->stats.exchange_bytes += (uint64_t)(n_sub - 1) * blk * sizeof(amp);
+    return QCSIM_OK;
+  }
+  QCSIM_TRY(ensure_stage(h, chunk, n_sub - 1));
   CUDA_TRY(cudaEventRecord(e0, h->stream));
   const uint64_t n_chunks = (blk + chunk - 1) / chunk;
   bool copied[2] = {false, false};
