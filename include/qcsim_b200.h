@@ -77,6 +77,8 @@ typedef struct qcsim_stats {
   uint64_t exchange_calls;  /* global<->local qubit exchanges (sharded registers) */
   uint64_t exchange_bytes;  /* bytes sent over NVLink by this rank */
   double exchange_ms;       /* device time spent in exchanges (CUDA events) */
+  uint64_t fused_rounds;    /* register rounds executed inside fused gate-block passes */
+  uint64_t fused_ops;       /* gate applications executed inside fused gate-block passes */
 } qcsim_stats;
 
 const char* qcsim_last_error(void);

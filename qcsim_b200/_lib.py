@@ -41,7 +41,7 @@ class Stats(C.Structure):
 
     _fields_ = [("gates_applied", C.c_uint64), ("kernel_launches", C.c_uint64), ("state_passes", C.c_uint64),
                 ("bytes_moved", C.c_uint64), ("exchange_calls", C.c_uint64), ("exchange_bytes", C.c_uint64),
-                ("exchange_ms", C.c_double)]
+                ("exchange_ms", C.c_double), ("fused_rounds", C.c_uint64), ("fused_ops", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -105,6 +105,13 @@ def load() -> C.CDLL:
         raise ImportError(
             f"{LIB_PATH} is missing: build it with `python -m qcsim_b200.build` (needs nvcc). "
             "qcsim_b200 has no CPU fallback.")
+    try:
+        # libqcsim_b200.so links libnccl.so.2; torch bundles a newer build under the same soname.
+        # Whichever is loaded first serves the whole process, and libtorch_cuda needs its own one:
+        # let torch load it first (torch is plumbing here: device memory, streams, torch.distributed).
+        import torch  # noqa: F401
+    except ImportError:
+        pass
     lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError here == ABI mismatch, which must be loud

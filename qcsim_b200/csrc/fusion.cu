@@ -27,208 +27,148 @@ int env_int(const char* name, int dflt) {
 
 }  // namespace
 
-// Build the parameter-block descriptor for one pass and launch it.
+// ---- round matrices ---------------------------------------------------------------------------------
+
+// Applies `op` to the 8 amplitudes spanned by a round's bits.  rpos[q] = register bit of qubit q
+// (-1: not a round qubit, then vval[q] is its value for this matrix variant).
+static void apply_small(const Op& op, const int* rpos, const int* vval, cplx* vec) {
+  uint32_t cmask = 0;
+  for (int i = 0; i < op.n_ctrl; ++i) {
+    const int q = op.ctrl[i];
+    if (rpos[q] >= 0) cmask |= 1u << rpos[q];
+    else if (!vval[q]) return;  // this variant has the control at 0: identity
+  }
+  auto live = [&](uint32_t x) { return (x & cmask) == cmask; };
+  switch (op.kind) {
+    case OP_PAIR: {
+      const uint32_t b0 = 1u << rpos[op.tgt[0]];
+      const uint32_t b1 = op.n_tgt == 2 ? 1u << rpos[op.tgt[1]] : 0u;
+      for (uint32_t x = 0; x < 8; ++x) {
+        if ((x & (b0 | b1)) || !live(x)) continue;
+        const uint32_t ia = op.n_tgt == 1 ? x : (x | b0), ib = op.n_tgt == 1 ? (x | b0) : (x | b1);
+        const cplx a = vec[ia], b = vec[ib];
+        vec[ia] = op.m[0] * a + op.m[1] * b;
+        vec[ib] = op.m[2] * a + op.m[3] * b;
+      }
+      break;
+    }
+    case OP_DENSE2:
+    case OP_DENSE3: {
+      const int nt = op.kind == OP_DENSE2 ? 2 : 3, d = 1 << nt;
+      uint32_t tm = 0, off[8];
+      for (int j = 0; j < nt; ++j) tm |= 1u << rpos[op.tgt[j]];
+      for (int c = 0; c < d; ++c) {
+        off[c] = 0;
+        for (int j = 0; j < nt; ++j)
+          if ((c >> j) & 1) off[c] |= 1u << rpos[op.tgt[j]];
+      }
+      for (uint32_t x = 0; x < 8; ++x) {
+        if ((x & tm) || !live(x)) continue;
+        cplx in[8], out[8];
+        for (int c = 0; c < d; ++c) in[c] = vec[x | off[c]];
+        for (int r = 0; r < d; ++r) {
+          cplx acc = op.m[r * d] * in[0];
+          for (int c = 1; c < d; ++c) acc += op.m[r * d + c] * in[c];
+          out[r] = acc;
+        }
+        for (int c = 0; c < d; ++c) vec[x | off[c]] = out[c];
+      }
+      break;
+    }
+    case OP_DIAG:
+      for (uint32_t x = 0; x < 8; ++x) {
+        if (!live(x)) continue;
+        int idx = 0;
+        for (int s = 0; s < op.n_tgt; ++s) {
+          const int q = op.tgt[s];
+          const int bit = rpos[q] >= 0 ? (int)((x >> rpos[q]) & 1u) : vval[q];
+          idx |= bit << s;
+        }
+        vec[x] *= op.m[idx];
+      }
+      break;
+    default: break;
+  }
+}
+
+int fusion_reserve(qcsim_sv*) { return QCSIM_OK; }
+void fusion_release(qcsim_sv*) {}
+
+// Build the round matrices + parameter block of one pass and launch it.  A launch holds at most
+// kMaxTileRounds rounds / kMaxTileMats matrices (parameter-block limit); a longer pass is cut into
+// several launches over the same tile set (each is still fp64-bound, not HBM-bound, at that length).
 static int launch_pass(qcsim_sv* h, const std::vector<Op>& all, const PassPlan& plan, int L) {
   const int k = (int)plan.tile.size();
   int local_of[64];
   for (int q = 0; q < 64; ++q) local_of[q] = -1;
   for (int j = 0; j < k; ++j) local_of[plan.tile[j]] = j;
 
-  std::vector<TileRound> rounds;
-  std::vector<TileOp> tops;
-  std::vector<amp> pool;
-
-  auto finish_round = [&](TileRound& rd, int nrb) {
-    // pad to exactly kRoundBits distinct ascending local bits
-    int bits[4];
-    int n = nrb;
-    for (int i = 0; i < nrb; ++i) bits[i] = rd.rb[i];
-    for (int cand = 0; n < kRoundBits && cand < k; ++cand) {
-      bool used = false;
-      for (int i = 0; i < n; ++i) used |= (bits[i] == cand);
-      if (!used) bits[n++] = cand;
-    }
-    std::sort(bits, bits + n);
-    for (int i = 0; i < n; ++i) rd.rb[i] = bits[i];
-  };
-
-  // ---- cut into rounds: greedy on the union of target bits
-  struct Pending {
-    int op;
-    int lt[3];
-    int nlt;
-  };
-  std::vector<std::vector<Pending>> round_ops;
-  std::vector<std::vector<int>> round_bits;
-  {
-    std::vector<Pending> cur;
-    std::vector<int> bits;
-    for (int idx : plan.ops) {
-      const Op& op = all[idx];
-      Pending p;
-      p.op = idx;
-      p.nlt = 0;
-      if (op.kind != OP_DIAG)
-        for (int i = 0; i < op.n_tgt; ++i) p.lt[p.nlt++] = local_of[op.tgt[i]];
-      std::vector<int> u = bits;
-      for (int i = 0; i < p.nlt; ++i)
-        if (std::find(u.begin(), u.end(), p.lt[i]) == u.end()) u.push_back(p.lt[i]);
-      if ((int)u.size() > kRoundBits) {
-        round_ops.push_back(cur);
-        round_bits.push_back(bits);
-        cur.clear();
-        bits.clear();
-        for (int i = 0; i < p.nlt; ++i) bits.push_back(p.lt[i]);
-      } else {
-        bits = u;
-      }
-      cur.push_back(p);
-    }
-    if (!cur.empty()) {
-      round_ops.push_back(cur);
-      round_bits.push_back(bits);
-    }
-  }
-
-  for (size_t r = 0; r < round_ops.size(); ++r) {
-    TileRound rd;
-    std::memset(&rd, 0, sizeof rd);
-    const int nrb = (int)round_bits[r].size();
-    for (int i = 0; i < nrb; ++i) rd.rb[i] = round_bits[r][i];
-    finish_round(rd, nrb);
-    int reg_of[16];
-    for (int j = 0; j < 16; ++j) reg_of[j] = -1;
-    for (int i = 0; i < kRoundBits; ++i) reg_of[rd.rb[i]] = i;
-    rd.op_begin = (int)tops.size();
-    for (const Pending& p : round_ops[r]) {
-      const Op& op = all[p.op];
-      TileOp t;
-      std::memset(&t, 0, sizeof t);
-      t.moff = (int)pool.size();
-      // controls: round bit / other tile bit / outside the tile
-      for (int i = 0; i < op.n_ctrl; ++i) {
-        const int q = op.ctrl[i];
-        const int lb = local_of[q];
-        if (lb < 0) t.gctrl |= 1ULL << q;
-        else if (reg_of[lb] >= 0) t.rctrl |= 1u << reg_of[lb];
-        else t.lctrl |= 1u << lb;
-      }
-      auto push = [&](const cplx& z) { pool.push_back(make_amp(z.real(), z.imag())); };
-      switch (op.kind) {
-        case OP_PAIR:
-          if (op.n_tgt == 1) {
-            const cplx *m = op.m;
-            const bool real = m[0].imag() == 0 && m[1].imag() == 0 && m[2].imag() == 0 && m[3].imag() == 0;
-            const bool rim = m[0].imag() == 0 && m[3].imag() == 0 && m[1].real() == 0 && m[2].real() == 0;
-            const bool isx = m[0] == cplx(0, 0) && m[3] == cplx(0, 0) && m[1] == cplx(1, 0) && m[2] == cplx(1, 0);
-            t.kind = isx ? TK_PAIR1_X : real ? TK_PAIR1_REAL : rim ? TK_PAIR1_RIM : TK_PAIR1;
-            t.r0 = reg_of[p.lt[0]];
-            for (int i = 0; i < 4; ++i) push(op.m[i]);
-          } else {
-            const bool issw = op.m[0] == cplx(0, 0) && op.m[3] == cplx(0, 0) && op.m[1] == cplx(1, 0) && op.m[2] == cplx(1, 0);
-            t.kind = issw ? TK_PAIR2_SWAP : TK_PAIR2;
-            int a = reg_of[p.lt[0]], b = reg_of[p.lt[1]];
-            if (a < b) {
-              t.r0 = a;
-              t.r1 = b;
-              for (int i = 0; i < 4; ++i) push(op.m[i]);
-            } else {  // swap the roles of the two amplitudes of the pair
-              t.r0 = b;
-              t.r1 = a;
-              push(op.m[3]);
-              push(op.m[2]);
-              push(op.m[1]);
-              push(op.m[0]);
-            }
-          }
-          break;
-        case OP_DENSE2: {
-          t.kind = TK_DENSE2;
-          int a = reg_of[p.lt[0]], b = reg_of[p.lt[1]];
-          const bool flip = a > b;  // matrix bit0 <-> r0, bit1 <-> r1 with r0 < r1
-          t.r0 = flip ? b : a;
-          t.r1 = flip ? a : b;
-          auto perm = [&](int i) { return flip ? (((i & 1) << 1) | ((i >> 1) & 1)) : i; };
-          for (int r2 = 0; r2 < 4; ++r2)
-            for (int c = 0; c < 4; ++c) push(op.m[perm(r2) * 4 + perm(c)]);
-          break;
-        }
-        case OP_DENSE3: {
-          t.kind = TK_DENSE3;
-          int rr[3] = {reg_of[p.lt[0]], reg_of[p.lt[1]], reg_of[p.lt[2]]};
-          // register index x has bit rr[j] <-> matrix bit j
-          auto perm = [&](int x) {
-            int mi = 0;
-            for (int j = 0; j < 3; ++j)
-              if ((x >> rr[j]) & 1) mi |= 1 << j;
-            return mi;
-          };
-          for (int r2 = 0; r2 < 8; ++r2)
-            for (int c = 0; c < 8; ++c) push(op.m[perm(r2) * 8 + perm(c)]);
-          break;
-        }
-        case OP_DIAG: {
-          t.kind = op.n_tgt == 0 ? TK_PHASE : TK_DIAG;
-          t.nsel = op.n_tgt;
-          for (int i = 0; i < op.n_tgt; ++i) {
-            const int q = op.tgt[i];
-            const int lb = local_of[q];
-            if (lb < 0) {
-              t.sel_src[i] = 2;
-              t.sel_pos[i] = q;
-            } else if (reg_of[lb] >= 0) {
-              t.sel_src[i] = 0;
-              t.sel_pos[i] = reg_of[lb];
-            } else {
-              t.sel_src[i] = 1;
-              t.sel_pos[i] = lb;
-            }
-          }
-          for (int i = 0; i < 8; ++i) push(i < (1 << op.n_tgt) ? op.m[i] : cplx(1, 0));
-          break;
-        }
-        default: break;
-      }
-      tops.push_back(t);
-    }
-    rd.op_end = (int)tops.size();
-    rounds.push_back(rd);
-  }
-
-  // ---- descriptor -> kernel parameter block
-  if (rounds.size() > (size_t)kMaxTileRounds || tops.size() > (size_t)kMaxTileOps || pool.size() > (size_t)kMaxTilePool)
-    return fail(QCSIM_ERR_BAD_ARG, "internal: pass too large (%zu rounds, %zu ops, %zu pool)", rounds.size(), tops.size(), pool.size());
-  static thread_local TilePassArgs A;  // 12 KiB: keep it off the stack; the launch copies it
+  const std::vector<RoundPlan> rplan = schedule_rounds(all, plan, kMaxVariantBits);
+  static thread_local TilePassArgs A;  // ~30 KiB: keep it off the stack; the launch copies it
   A.k = k;
-  A.n_rounds = (int)rounds.size();
   A.low_identity = L;
   A.n_tiles = 1ULL << (h->n_local - k);
   for (int j = 0; j < kMaxTileBits; ++j) A.tpos[j] = j < k ? plan.tile[j] : 0;
-  for (size_t r = 0; r < rounds.size(); ++r) {
-    A.rounds[r].x = (unsigned)(rounds[r].rb[0] | (rounds[r].rb[1] << 8) | (rounds[r].rb[2] << 16));
-    A.rounds[r].y = (unsigned)(rounds[r].op_begin | (rounds[r].op_end << 16));
-  }
-  for (size_t o = 0; o < tops.size(); ++o) pack_tile_op(tops[o], &A.ops[2 * o]);
-  for (size_t i = 0; i < pool.size(); ++i) A.pool[i] = pool[i];
   const size_t smem = (size_t)sizeof(amp) << k;
-  static const int variant = env_int("QCSIM_TILE_VARIANT", 0);  // 0: NI=1/128 regs, 1: NI=1/80 regs, 2: NI=2/128 regs
   static bool attr_set = false;
   if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(k_tile_pass<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    CUDA_TRY(cudaFuncSetAttribute(k_tile_pass<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    CUDA_TRY(cudaFuncSetAttribute(k_tile_pass<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(k_tile_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     attr_set = true;
   }
-  const int by_smem = std::max(1, (int)((220 * 1024) / (smem + 1024)));
-  const int per_sm = std::min(by_smem, variant == 1 ? 3 : 2);
+  const int per_sm = std::max(1, std::min(2, (int)((220 * 1024) / (smem + 1024))));
   const uint64_t grid = std::min<uint64_t>(A.n_tiles, (uint64_t)kNumSMs * per_sm);
-  if (variant == 2 && k == 12) k_tile_pass<2, 2><<<(unsigned)grid, kTileThreads, smem, h->stream>>>(h->psi, A);
-  else if (variant == 1) k_tile_pass<1, 3><<<(unsigned)grid, kTileThreads, smem, h->stream>>>(h->psi, A);
-  else k_tile_pass<1, 2><<<(unsigned)grid, kTileThreads, smem, h->stream>>>(h->psi, A);
-  CUDA_TRY(cudaGetLastError());
-  h->stats.kernel_launches += 1;
-  h->stats.state_passes += 1;
-  h->stats.bytes_moved += 32ULL * h->dim_local;
+  static const int debug = env_int("QCSIM_DEBUG_PLAN", 0);
+
+  size_t r = 0;
+  while (r < rplan.size()) {
+    int n_rounds = 0;
+    size_t mat_index = 0, n_ops = 0;
+    while (r < rplan.size() && n_rounds < kMaxTileRounds && mat_index + ((size_t)1 << rplan[r].vq.size()) <= (size_t)kMaxTileMats) {
+      const RoundPlan& rp = rplan[r];
+      int rpos[64];
+      for (int q = 0; q < 64; ++q) rpos[q] = -1;
+      for (int j = 0; j < 3; ++j) rpos[plan.tile[rp.rbits[j]]] = j;
+      const int nv = (int)rp.vq.size();
+      for (int a = 0; a < (1 << nv); ++a) {
+        int vval[64];
+        for (int q = 0; q < 64; ++q) vval[q] = 0;
+        for (int j = 0; j < nv; ++j) vval[rp.vq[j]] = (a >> j) & 1;
+        amp* M = A.mats + (mat_index + a) * kRoundMatAmps;
+        for (int col = 0; col < 8; ++col) {
+          cplx vec[8];
+          for (int x = 0; x < 8; ++x) vec[x] = cplx(x == col ? 1.0 : 0.0, 0.0);
+          for (int idx : rp.ops) apply_small(all[idx], rpos, vval, vec);
+          for (int row = 0; row < 8; ++row) M[row * 8 + col] = make_amp(vec[row].real(), vec[row].imag());
+        }
+      }
+      TileRoundDesc& rd = A.rounds[n_rounds];
+      rd.rb = (uint32_t)(rp.rbits[0] | (rp.rbits[1] << 8) | (rp.rbits[2] << 16));
+      for (int w = 0; w < 3; ++w) rd.tb[w] = 0;
+      for (int j = 0; j < 9; ++j) rd.tb[j >> 2] |= (uint32_t)rp.item_bit[j] << (8 * (j & 3));
+      rd.var = (uint32_t)nv;
+      for (int j = 0; j < nv; ++j) {
+        const int q = rp.vq[j];
+        const uint32_t e = local_of[q] >= 0 ? (uint32_t)(local_of[q] << 1) : (uint32_t)((q << 1) | 1);
+        rd.var |= e << (8 + 8 * j);
+      }
+      rd.mat_off = (uint32_t)mat_index;
+      rd.pad[0] = rd.pad[1] = 0;
+      mat_index += (size_t)1 << nv;
+      n_ops += rp.ops.size();
+      ++n_rounds;
+      ++r;
+    }
+    A.n_rounds = n_rounds;
+    k_tile_pass<<<(unsigned)grid, kTileThreads, smem, h->stream>>>(h->psi, A);
+    CUDA_TRY(cudaGetLastError());
+    h->stats.kernel_launches += 1;
+    h->stats.state_passes += 1;
+    h->stats.bytes_moved += 32ULL * h->dim_local;
+    h->stats.fused_rounds += n_rounds;
+    h->stats.fused_ops += n_ops;
+    if (debug > 1)
+      std::fprintf(stderr, "[qcsim pass] k=%d L=%d ops=%zu rounds=%d matrices=%zu\n", k, L, n_ops, n_rounds, mat_index);
+  }
   return QCSIM_OK;
 }
 
@@ -251,7 +191,7 @@ int fusion_execute_local(qcsim_sv* h, const std::vector<Op>& ops) {
     return QCSIM_OK;
   }
 
-  const std::vector<PlanStep> steps = plan_passes(ops, nl, K, L, kMaxTileOps, kMaxTilePool);
+  const std::vector<PlanStep> steps = plan_passes(ops, nl, K, L, 1 << 20, 1 << 30);
   static const int debug = env_int("QCSIM_DEBUG_PLAN", 0);
   if (debug) {
     int nf = 0, absorbed = 0;
@@ -275,7 +215,5 @@ int fusion_execute_local(qcsim_sv* h, const std::vector<Op>& ops) {
   return QCSIM_OK;
 }
 
-int fusion_reserve(qcsim_sv*) { return QCSIM_OK; }
-void fusion_release(qcsim_sv*) {}
 
 }  // namespace qcsim

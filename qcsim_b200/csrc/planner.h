@@ -128,4 +128,99 @@ inline std::vector<PlanStep> plan_passes(const std::vector<Op>& ops, int n_local
   return steps;
 }
 
+// ---- rounds inside a fused pass --------------------------------------------------------------------
+// A round = 3 tile bits held in registers (8 amplitudes per thread) + the ops folded into its 8x8
+// matrix + up to 3 "variant" qubits (controls / diagonal selectors that are not round bits; each
+// doubles the number of matrices of the round).  Ops are taken in program order but may jump ahead
+// of ops they commute with (same rule as plan_passes).
+struct RoundPlan {
+  int rbits[3];            // tile-local bit held by register bit j
+  std::vector<int> vq;     // variant qubits (register qubit numbers), <= 3
+  int item_bit[9];         // tile-local bit walked by item-index bit j (first k - 3 entries valid)
+  std::vector<int> ops;    // indices into the op list, program order
+};
+
+inline std::vector<RoundPlan> schedule_rounds(const std::vector<Op>& all, const PassPlan& plan, int max_variant_bits = 3) {
+  const int k = (int)plan.tile.size();
+  int local_of[64];
+  for (int q = 0; q < 64; ++q) local_of[q] = -1;
+  for (int j = 0; j < k; ++j) local_of[plan.tile[j]] = j;
+
+  std::vector<int> remaining = plan.ops;
+  std::vector<RoundPlan> rounds;
+  while (!remaining.empty()) {
+    uint64_t R = 0, V = 0;  // round qubits / variant qubits (masks over register qubits)
+    RoundPlan rp;
+    std::vector<int> left;
+    uint64_t blocked_nd = 0, blocked_d = 0;
+    for (int idx : remaining) {
+      const OpMasks m = masks_of(all[idx]);
+      const bool conflict = ((m.nd | m.dg) & blocked_nd) != 0 || (m.nd & blocked_d) != 0;
+      if (!conflict) {
+        const uint64_t nR = R | m.nd;
+        const uint64_t nV = (V | m.dg) & ~nR;
+        if (__builtin_popcountll(nR) <= 3 && __builtin_popcountll(nV) <= max_variant_bits) {
+          R = nR;
+          V = nV;
+          rp.ops.push_back(idx);
+          continue;
+        }
+      }
+      left.push_back(idx);
+      blocked_nd |= m.nd;
+      blocked_d |= m.dg;
+    }
+    // free register slots: promote variant qubits that live in the tile (halves the matrix count
+    // for free), then pad with unused tile bits
+    for (int q = 0; q < 64 && __builtin_popcountll(R) < 3; ++q)
+      if (((V >> q) & 1ULL) && local_of[q] >= 0) {
+        R |= 1ULL << q;
+        V &= ~(1ULL << q);
+      }
+    for (int j = k - 1; j >= 0 && __builtin_popcountll(R) < 3; --j) R |= 1ULL << plan.tile[j];
+    int nr = 0;
+    uint32_t used = 0;
+    for (int q = 0; q < 64; ++q)
+      if ((R >> q) & 1ULL) {
+        rp.rbits[nr++] = local_of[q];
+        used |= 1u << local_of[q];
+      }
+    for (int q = 0; q < 64; ++q)
+      if ((V >> q) & 1ULL) rp.vq.push_back(q);
+    // item-index bits.  Variant qubits inside the tile go to the warp-index part of the item index
+    // (bits 5..7: warp-uniform matrix choice; bit 8 pairs the two items a thread processes with one
+    // set of matrix loads, so it must not select the matrix); the low three item bits get distinct
+    // (position mod 3) so a quarter-warp's 128-bit shared-memory accesses land in 8 distinct bank
+    // groups under swz().
+    const int ni = k - 3;
+    int order[16];
+    for (int j = 0; j < 16; ++j) order[j] = -1;
+    int top = ni >= 9 ? 7 : ni - 1;
+    std::vector<int> rest;
+    for (int lb = 0; lb < k; ++lb) {
+      if ((used >> lb) & 1u) continue;
+      if ((V >> plan.tile[lb]) & 1ULL) order[top--] = lb;
+      else rest.push_back(lb);
+    }
+    int pos = 0;
+    auto next_free = [&]() {
+      while (order[pos] >= 0) ++pos;
+      return pos;
+    };
+    for (int res = 0; res < 3; ++res)
+      for (size_t i = 0; i < rest.size(); ++i)
+        if (rest[i] >= 0 && rest[i] % 3 == res) {
+          order[next_free()] = rest[i];
+          rest[i] = -1;
+          break;
+        }
+    for (int lb : rest)
+      if (lb >= 0) order[next_free()] = lb;
+    for (int j = 0; j < 9; ++j) rp.item_bit[j] = (j < ni && order[j] >= 0) ? order[j] : 0;
+    rounds.push_back(rp);
+    remaining.swap(left);
+  }
+  return rounds;
+}
+
 }  // namespace qcsim
