@@ -72,6 +72,15 @@ __device__ __forceinline__ void st_amp2(amp* p, amp2 v) {
                : "memory");
 }
 
+// ---- shared-memory tiles (tile_kernels.cuh, qft_kernels.cuh) ---------------------------------------
+constexpr int kMaxTileBits = 12;   // 2^12 x 16 B = 64 KiB of shared memory per tile
+constexpr int kTileThreads = 256;
+
+// 16-byte slot swizzle, linear over XOR: folds every 3-bit group of the index onto the low 3
+// bits, so any 8 indices that differ in 3 bits with distinct (position mod 3) hit 8 distinct
+// 16-byte bank groups.  The host picks which tile bits the low 3 item-index bits walk over.
+__host__ __device__ __forceinline__ uint32_t swz(uint32_t j) { return j ^ ((j >> 3) & 7u) ^ ((j >> 6) & 7u) ^ ((j >> 9) & 7u); }
+
 // ---- double-double (error-free) accumulation, used by the measurement scan -----------------
 struct dd {
   double hi, lo;

@@ -19,6 +19,7 @@
 #include "dist.h"
 #include "dist_plan.h"
 #include "fusion.h"
+#include "qft_kernels.cuh"
 #include "reduce_kernels.cuh"
 
 namespace qcsim {
@@ -399,6 +400,51 @@ int dist_canonicalize(qcsim_sv* h) {
   DistState* d = st(h);
   if (d->layout.is_identity()) return QCSIM_OK;
   return run_steps(h, dist_plan_canonicalize(d->layout));
+}
+
+// QFT / IQFT on a sharded register (see engine_qft).  The transform's local part runs as radix-8
+// passes on every shard; the qubits that live on global positions are brought down with ONE
+// exchange, transformed in one pass whose twiddles read the rank bits, and sent back -- two
+// all-to-all phases in total.  The qubit reversal stays a relabelling.
+int dist_qft(qcsim_sv* h, int sq, int eq, bool do_swap, bool inverse, int* handled) {
+  DistState* d = st(h);
+  DistLayout& Lo = d->layout;
+  const int nl = h->n_local;
+  *handled = 0;
+  if (sq >= nl) return QCSIM_OK;  // transform entirely on global qubits: gate-by-gate path
+  auto virtual_swaps = [&]() {
+    for (int s = sq, e = eq; s < e; ++s, --e) Lo.swap_logical(s, e);
+  };
+  if (inverse && do_swap) virtual_swaps();  // QubitsSwapper first (QuantumFourierTransform.h:67)
+  QCSIM_TRY(dist_canonicalize(h));          // the passes below assume logical == physical
+  const QftSegment ident = {0, h->n, 0, 0};
+  const int gg = eq >= nl ? eq - nl + 1 : 0;  // transform qubits on global positions
+  const int leq = std::min(eq, nl - 1);
+  DistStep ex;
+  ex.exchange = true;
+  ex.k = gg;
+  for (int j = 0; j < gg; ++j) {
+    ex.gpos[j] = nl + j;
+    ex.lpos[j] = nl - gg + j;
+  }
+  QftSegment seg[2] = {{0, nl - gg, 0, 0}, {nl, gg, nl - gg, 0}};
+  auto top_pass = [&]() -> int {
+    // global positions nl..eq <-> local positions nl-gg..nl-1, transform there, and back
+    QCSIM_TRY(do_exchange(h, ex));
+    QCSIM_TRY(engine_qft_passes(h, nl - gg, nl - 1, inverse, (uint64_t)h->rank << nl, seg, 2, gg, sq));
+    QCSIM_TRY(do_exchange(h, ex));
+    return QCSIM_OK;
+  };
+  if (!inverse) {
+    if (gg) QCSIM_TRY(top_pass());
+    QCSIM_TRY(engine_qft_passes(h, sq, leq, false, 0, &ident, 1, 0, sq));
+    if (do_swap) virtual_swaps();
+  } else {
+    QCSIM_TRY(engine_qft_passes(h, sq, leq, true, 0, &ident, 1, 0, sq));
+    if (gg) QCSIM_TRY(top_pass());
+  }
+  *handled = 1;
+  return QCSIM_OK;
 }
 
 void dist_collect_stats(qcsim_sv* h) {

@@ -16,6 +16,8 @@ int dist_allreduce_host(qcsim_sv* h, double* vals, int count);
 int dist_apply(qcsim_sv* h, const Op& op);
 int dist_canonicalize(qcsim_sv* h);
 int dist_pick_state(qcsim_sv* h, double prob, uint64_t fallback, uint64_t* outcome);
+// fast QFT on a sharded register; *handled = 0 when the caller must fall back to the gate-by-gate path
+int dist_qft(qcsim_sv* h, int sq, int eq, bool do_swap, bool inverse, int* handled);
 void dist_collect_stats(qcsim_sv* h);  // resolves the CUDA-event timings of finished exchanges into stats.exchange_ms
 
 }  // namespace qcsim

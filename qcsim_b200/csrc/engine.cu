@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "engine.h"
@@ -10,6 +11,7 @@
 #include "reduce_kernels.cuh"
 #include "dist.h"
 #include "fusion.h"
+#include "qft_kernels.cuh"
 
 namespace qcsim {
 
@@ -419,12 +421,185 @@ static void swap_matrix(double* m) {  // QuantumGate.h:10-28
   m[30] = 1.0;
 }
 
-int engine_qft(qcsim_sv* h, uint64_t sq_, uint64_t eq_, bool do_swap, bool inverse) {
-  // sub-register clamp as in QuantumSubAlgorithmOnSubregister (QuantumAlgorithm.h): eq = max(sq, min(N-1, eq))
-  const uint64_t nm1 = (uint64_t)h->n - 1;
-  if (sq_ > nm1) return fail(QCSIM_ERR_QUBIT_TOO_HIGH, "Qubit number is too high");
-  const int sq = (int)sq_;
-  const int eq = (int)std::max<uint64_t>(sq_, std::min<uint64_t>(nm1, eq_));
+// item-index bits of a round whose register bits are `reg_mask` (tile-local): the other tile bits in
+// an order whose low three have distinct (position mod 3), see swz()
+static void item_bit_order(int k, uint32_t reg_mask, uint32_t* words, int n_words) {
+  int rest[16], nrest = 0, order[16], n = 0;
+  for (int lb = 0; lb < k; ++lb)
+    if (!((reg_mask >> lb) & 1u)) rest[nrest++] = lb;
+  for (int res = 0; res < 3; ++res)
+    for (int i = 0; i < nrest; ++i)
+      if (rest[i] >= 0 && rest[i] % 3 == res) {
+        order[n++] = rest[i];
+        rest[i] = -1;
+        break;
+      }
+  for (int i = 0; i < nrest; ++i)
+    if (rest[i] >= 0) order[n++] = rest[i];
+  for (int w = 0; w < n_words; ++w) words[w] = 0;
+  for (int j = 0; j < n && j < 4 * n_words; ++j) words[j >> 2] |= (uint32_t)order[j] << (8 * (j & 3));
+}
+
+// QFT / IQFT on the LOCAL physical positions [sq, eq] as radix-8 FFT passes (qft_kernels.cuh).
+// `seg` maps a physical index (local bits | rank_bits) to the logical value of the qubits, for
+// the twiddle exponent; on one GPU it is the identity.
+int engine_qft_passes(qcsim_sv* h, int sq, int eq, bool inverse, uint64_t rank_bits, const QftSegment* seg, int n_seg,
+                      int logical_shift, int r_floor) {
+  const int nl = h->n_local;
+  const int m = eq - sq + 1;
+  struct Grp { int top, size; };
+  std::vector<Grp> groups;  // top-down
+  for (int top = eq; top >= sq;) {
+    const int size = std::min(3, top - sq + 1);
+    groups.push_back({top, size});
+    top -= size;
+  }
+  (void)m;
+  const int Kmax = std::min(kMaxTileBits, nl);
+  const int Lmin = std::min(3, nl);
+  struct Pass { std::vector<int> tile; std::vector<Grp> groups; };
+  std::vector<Pass> passes;
+  for (size_t i = 0; i < groups.size();) {
+    uint64_t bits = (1ULL << Lmin) - 1ULL;
+    Pass p;
+    while (i < groups.size() && (int)p.groups.size() < kMaxQftGroups) {
+      uint64_t gb = 0;
+      for (int j = 0; j < groups[i].size; ++j) gb |= 1ULL << (groups[i].top - j);
+      if (__builtin_popcountll(bits | gb) > Kmax) break;
+      bits |= gb;
+      p.groups.push_back(groups[i]);
+      ++i;
+    }
+    if (p.groups.empty()) return fail(QCSIM_ERR_BAD_ARG, "internal: QFT group does not fit a tile");
+    for (int q = 0; q < nl && __builtin_popcountll(bits) < Kmax; ++q) bits |= 1ULL << q;  // pad: longer contiguous runs
+    for (int q = 0; q < nl; ++q)
+      if ((bits >> q) & 1ULL) p.tile.push_back(q);
+    passes.push_back(p);
+  }
+  if (inverse) {
+    std::reverse(passes.begin(), passes.end());
+    for (Pass& p : passes) std::reverse(p.groups.begin(), p.groups.end());
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(k_qft_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(k_tile_permute, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    attr_set = true;
+  }
+  const double pi = 3.14159265358979323846;
+  for (const Pass& p : passes) {
+    QftPassArgs A;
+    std::memset(&A, 0, sizeof A);
+    const int k = (int)p.tile.size();
+    A.k = k;
+    int L = 0;
+    while (L < k && p.tile[L] == L) ++L;
+    A.low_identity = L;
+    A.n_groups = (int)p.groups.size();
+    A.inverse = inverse ? 1 : 0;
+    A.n_tiles = 1ULL << (nl - k);
+    A.rank_bits = rank_bits;
+    for (int j = 0; j < kMaxTileBits; ++j) A.tpos[j] = j < k ? p.tile[j] : 0;
+    A.sq = r_floor;  // logical start qubit of the whole transform
+    A.n_seg = n_seg;
+    for (int i = 0; i < n_seg; ++i) A.seg[i] = seg[i];
+    A.s = 1. / std::sqrt(2.);
+    const double sign = inverse ? -1.0 : 1.0;
+    A.ph2 = make_amp(std::cos(sign * pi / 2), std::sin(sign * pi / 2));  // std::polar(1., theta)
+    A.ph4 = make_amp(std::cos(sign * pi / 4), std::sin(sign * pi / 4));
+    for (size_t g = 0; g < p.groups.size(); ++g) {
+      QftGroup& G = A.groups[g];
+      G.size = p.groups[g].size;
+      G.top_qubit = p.groups[g].top + logical_shift;
+      const int low_q = p.groups[g].top - G.size + 1;
+      int lbit = 0;
+      while (p.tile[lbit] != low_q) ++lbit;
+      G.lbit = lbit;
+      const uint32_t reg_mask = ((1u << G.size) - 1u) << lbit;
+      item_bit_order(k, reg_mask, G.tb, 3);
+    }
+    const size_t smem = sizeof(amp) << k;
+    const uint64_t grid = std::min<uint64_t>(A.n_tiles, (uint64_t)kNumSMs * 2);
+    k_qft_pass<<<(unsigned)grid, kTileThreads, smem, h->stream>>>(h->psi, A);
+    CUDA_TRY(cudaGetLastError());
+    count_pass(h, h->dim_local);
+    h->stats.fused_rounds += p.groups.size();
+  }
+  return QCSIM_OK;
+}
+
+// In-place permutation of LOCAL physical index bits: afterwards position p holds what position
+// src_of[p] held (src_of is a permutation of 0..n_local-1, identity where nothing moves).  The
+// permutation is written as a sequence of position swaps; consecutive swaps whose positions fit
+// one tile (with the low bits that keep HBM accesses contiguous) run as ONE in-tile permutation pass.
+int engine_permute_bits(qcsim_sv* h, const int* src_of) {
+  const int nl = h->n_local;
+  std::vector<std::pair<int, int>> swaps;
+  {
+    int cur[64];  // cur[p] = original position whose content is now at p
+    for (int p = 0; p < nl; ++p) cur[p] = p;
+    for (int p = 0; p < nl; ++p) {
+      if (cur[p] == src_of[p]) continue;
+      int q = -1;
+      for (int r = p + 1; r < nl; ++r)
+        if (cur[r] == src_of[p]) q = r;
+      if (q < 0) return fail(QCSIM_ERR_BAD_ARG, "internal: not a permutation");
+      swaps.push_back({p, q});
+      std::swap(cur[p], cur[q]);
+    }
+  }
+  if (swaps.empty()) return QCSIM_OK;
+  const int Kmax = std::min(kMaxTileBits, nl);
+  const uint64_t low = (1ULL << std::min(2, nl)) - 1ULL;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(k_tile_permute, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    attr_set = true;
+  }
+  size_t i = 0;
+  while (i < swaps.size()) {
+    uint64_t bits = low;
+    int perm[64];  // perm[p] = position (at the start of this pass) whose content ends up at p
+    for (int p = 0; p < 64; ++p) perm[p] = p;
+    while (i < swaps.size()) {
+      const uint64_t nb = bits | (1ULL << swaps[i].first) | (1ULL << swaps[i].second);
+      if (__builtin_popcountll(nb) > Kmax) break;
+      bits = nb;
+      std::swap(perm[swaps[i].first], perm[swaps[i].second]);
+      ++i;
+    }
+    for (int q = 0; q < nl && __builtin_popcountll(bits) < Kmax; ++q) bits |= 1ULL << q;  // pad: longer contiguous runs
+    PermPassArgs A;
+    std::memset(&A, 0, sizeof A);
+    int local_of[64], k = 0;
+    for (int q = 0; q < 64; ++q) local_of[q] = -1;
+    for (int q = 0; q < nl; ++q)
+      if ((bits >> q) & 1ULL) {
+        A.tpos[k] = q;
+        local_of[q] = k++;
+      }
+    A.k = k;
+    int L = 0;
+    while (L < k && A.tpos[L] == L) ++L;
+    A.low_identity = L;
+    A.n_tiles = 1ULL << (nl - k);
+    for (int j = 0; j < kMaxTileBits; ++j) A.src_bit[j] = j < k ? local_of[perm[A.tpos[j]]] : j;
+    const size_t smem = sizeof(amp) << k;
+    const uint64_t grid = std::min<uint64_t>(A.n_tiles, (uint64_t)kNumSMs * 2);
+    k_tile_permute<<<(unsigned)grid, kTileThreads, smem, h->stream>>>(h->psi, A);
+    CUDA_TRY(cudaGetLastError());
+    count_pass(h, h->dim_local);
+  }
+  return QCSIM_OK;
+}
+
+static uint64_t qft_gate_count(int m, bool do_swap) {
+  return (uint64_t)m + (uint64_t)m * (m - 1) / 2 + (do_swap ? (uint64_t)(m / 2) : 0);
+}
+
+// generic gate-by-gate expansion (QuantumFourierTransform.h:35-87, QubitsSwapper.h:23-34); used by
+// sharded registers in non-canonical layouts and by QCSIM_QFT_GENERIC=1
+static std::vector<Op> qft_gate_ops(int sq, int eq, bool do_swap, bool inverse) {
   double hm[8], cp[32], sw[32];
   hadamard_matrix(hm);
   swap_matrix(sw);
@@ -466,13 +641,56 @@ int engine_qft(qcsim_sv* h, uint64_t sq_, uint64_t eq_, bool do_swap, bool inver
     }
     H(eq);
   }
-  h->stats.gates_applied += ops.size();
+  return ops;
+}
+
+static int engine_qft_generic(qcsim_sv* h, int sq, int eq, bool do_swap, bool inverse) {
+  const std::vector<Op> ops = qft_gate_ops(sq, eq, do_swap, inverse);
   if (h->fusion) {
     for (const Op& op : ops) QCSIM_TRY(engine_enqueue(h, op));
     return QCSIM_OK;
   }
   QCSIM_TRY(engine_flush(h));
   return fusion_execute(h, ops);
+}
+
+int engine_reverse_bits(qcsim_sv* h, int sq, int eq) {
+  int src_of[64];
+  for (int p = 0; p < 64; ++p) src_of[p] = p;
+  for (int s = sq, e = eq; s < e; ++s, --e) {
+    src_of[s] = e;
+    src_of[e] = s;
+  }
+  return engine_permute_bits(h, src_of);
+}
+
+int engine_qft(qcsim_sv* h, uint64_t sq_, uint64_t eq_, bool do_swap, bool inverse) {
+  // sub-register clamp as in QuantumSubAlgorithmOnSubregister (QuantumAlgorithm.h): eq = max(sq, min(N-1, eq))
+  const uint64_t nm1 = (uint64_t)h->n - 1;
+  if (sq_ > nm1) return fail(QCSIM_ERR_QUBIT_TOO_HIGH, "Qubit number is too high");
+  const int sq = (int)sq_;
+  const int eq = (int)std::max<uint64_t>(sq_, std::min<uint64_t>(nm1, eq_));
+  h->stats.gates_applied += qft_gate_count(eq - sq + 1, do_swap);
+  static const bool generic = std::getenv("QCSIM_QFT_GENERIC") != nullptr;
+  if (generic) return engine_qft_generic(h, sq, eq, do_swap, inverse);
+  QCSIM_TRY(engine_flush(h));  // queued gates come first
+  return engine_qft_direct(h, sq, eq, do_swap, inverse);
+}
+
+// the transform itself, on qubits [sq, eq] (already validated, nothing queued before it)
+int engine_qft_direct(qcsim_sv* h, int sq, int eq, bool do_swap, bool inverse) {
+  if (h->world > 1) {
+    int handled = 0;
+    QCSIM_TRY(dist_qft(h, sq, eq, do_swap, inverse, &handled));
+    if (handled) return QCSIM_OK;
+    // transform entirely on global qubits: expand and run through the sharded gate path
+    return dist_execute(h, qft_gate_ops(sq, eq, do_swap, inverse));
+  }
+  const QftSegment ident = {0, h->n, 0, 0};
+  if (inverse && do_swap) QCSIM_TRY(engine_reverse_bits(h, sq, eq));
+  QCSIM_TRY(engine_qft_passes(h, sq, eq, inverse, 0, &ident, 1, 0, sq));
+  if (!inverse && do_swap) QCSIM_TRY(engine_reverse_bits(h, sq, eq));
+  return QCSIM_OK;
 }
 
 // ---- measurement scan ----------------------------------------------------------------------------

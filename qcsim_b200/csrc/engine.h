@@ -98,6 +98,12 @@ int engine_flush(qcsim_sv* h);
 void engine_drop_queue(qcsim_sv* h);
 int engine_canonicalize(qcsim_sv* h);
 int engine_qft(qcsim_sv* h, uint64_t sq, uint64_t eq, bool do_swap, bool inverse);
+struct QftSegment;
+int engine_qft_passes(qcsim_sv* h, int sq, int eq, bool inverse, uint64_t rank_bits, const QftSegment* seg, int n_seg,
+                      int logical_shift, int r_floor);
+int engine_permute_bits(qcsim_sv* h, const int* src_of);
+int engine_reverse_bits(qcsim_sv* h, int sq, int eq);
+int engine_qft_direct(qcsim_sv* h, int sq, int eq, bool do_swap, bool inverse);
 
 int engine_pick_state(qcsim_sv* h, double prob, uint64_t fallback, uint64_t* outcome);
 int engine_sample(qcsim_sv* h, const double* probs, uint64_t count, uint64_t* outcomes);

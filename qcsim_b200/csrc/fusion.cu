@@ -8,6 +8,7 @@
 //   * absorbed ops keep their relative order and are cut into rounds of <= 3 target bits;
 //   * a pass that would not save HBM traffic over running its ops one by one is not fused.
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -97,13 +98,12 @@ void fusion_release(qcsim_sv*) {}
 // Build the round matrices + parameter block of one pass and launch it.  A launch holds at most
 // kMaxTileRounds rounds / kMaxTileMats matrices (parameter-block limit); a longer pass is cut into
 // several launches over the same tile set (each is still fp64-bound, not HBM-bound, at that length).
-static int launch_pass(qcsim_sv* h, const std::vector<Op>& all, const PassPlan& plan, int L) {
+static int launch_pass(qcsim_sv* h, const std::vector<Op>& all, const PassPlan& plan, int L, const std::vector<RoundPlan>& rplan) {
   const int k = (int)plan.tile.size();
   int local_of[64];
   for (int q = 0; q < 64; ++q) local_of[q] = -1;
   for (int j = 0; j < k; ++j) local_of[plan.tile[j]] = j;
 
-  const std::vector<RoundPlan> rplan = schedule_rounds(all, plan, kMaxVariantBits);
   static thread_local TilePassArgs A;  // ~30 KiB: keep it off the stack; the launch copies it
   A.k = k;
   A.low_identity = L;
@@ -172,9 +172,35 @@ static int launch_pass(qcsim_sv* h, const std::vector<Op>& all, const PassPlan& 
   return QCSIM_OK;
 }
 
+static int execute_plain(qcsim_sv* h, const std::vector<Op>& ops) {
+  if (ops.empty()) return QCSIM_OK;
+  if (h->world > 1) return dist_execute(h, ops);
+  return fusion_execute_local(h, ops);
+}
+
 int fusion_execute(qcsim_sv* h, const std::vector<Op>& ops_in) {
-  if (h->world > 1) return dist_execute(h, ops_in);
-  return fusion_execute_local(h, ops_in);
+  // QFT / IQFT gate streams (QCSim's own QuantumFourierTransform emits them gate by gate) run as
+  // radix-8 FFT passes; everything around them goes through the gate-block planner
+  static const int no_qft = env_int("QCSIM_QFT_GENERIC", 0);
+  if (no_qft || ops_in.size() < 10) return execute_plain(h, ops_in);
+  std::vector<Op> plain;
+  size_t i = 0;
+  while (i < ops_in.size()) {
+    const Op& op = ops_in[i];
+    const bool candidate = op.n_ctrl == 0 && op.kind == OP_PAIR;  // a pattern starts with H or SWAP
+    QftMatch m;
+    if (candidate) m = match_qft(ops_in, i);
+    if (m.length > 0) {
+      QCSIM_TRY(execute_plain(h, plain));
+      plain.clear();
+      QCSIM_TRY(engine_qft_direct(h, m.sq, m.eq, m.do_swap, m.inverse));
+      i += m.length;
+    } else {
+      plain.push_back(op);
+      ++i;
+    }
+  }
+  return execute_plain(h, plain);
 }
 
 // All qubit indices in `ops` are physical bit positions of the local slice.
@@ -210,7 +236,20 @@ int fusion_execute_local(qcsim_sv* h, const std::vector<Op>& ops) {
     }
     int Lrun = 0;  // the low run of identity-mapped tile bits may be longer than L
     while (Lrun < (int)st.pass.tile.size() && st.pass.tile[Lrun] == Lrun) ++Lrun;
-    QCSIM_TRY(launch_pass(h, ops, st.pass, Lrun));
+    // A round costs fp64-pipe time worth ~24 B of HBM traffic per amplitude; a pass whose rounds cost
+    // more than running its gates one by one (long runs of cheap diagonal gates) is not fused
+    const std::vector<RoundPlan> rplan = schedule_rounds(ops, st.pass, kMaxVariantBits);
+    size_t n_mats = 0;
+    for (const RoundPlan& rp : rplan) n_mats += (size_t)1 << rp.vq.size();
+    const double launches = std::max(std::ceil(rplan.size() / (double)kMaxTileRounds), std::ceil(n_mats / (double)kMaxTileMats));
+    const double cost_fused = std::max(32.0 * launches, 24.0 * rplan.size());
+    double cost_alone = 0;
+    for (int idx : st.pass.ops) cost_alone += standalone_cost(ops[idx]);
+    if (cost_fused >= cost_alone) {
+      for (int idx : st.pass.ops) QCSIM_TRY(engine_launch_local(h, ops[idx]));
+      continue;
+    }
+    QCSIM_TRY(launch_pass(h, ops, st.pass, Lrun, rplan));
   }
   return QCSIM_OK;
 }

@@ -8,6 +8,8 @@
 // commute, i.e. on every qubit they share both act diagonally (control or diagonal selector).
 #pragma once
 
+#include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <vector>
 
@@ -221,6 +223,137 @@ inline std::vector<RoundPlan> schedule_rounds(const std::vector<Op>& all, const 
     remaining.swap(left);
   }
   return rounds;
+}
+
+// ---- QFT recognition ---------------------------------------------------------------------------------
+// QCSim's own QuantumFourierTransform (QuantumFourierTransform.h:35-87) reaches the engine as a
+// stream of H / ControlledPhaseShift / SWAP gates.  The exact stream -- same order, the reference's
+// own phases (M_PI_2 halved repeatedly through std::polar) -- is recognised here so that it runs
+// as radix-8 FFT passes (qft_kernels.cuh) instead of hundreds of diagonal gates.
+struct QftMatch {
+  int length = 0;  // ops consumed (0: no match)
+  int sq = 0, eq = 0;
+  bool do_swap = false, inverse = false;
+};
+
+namespace detail {
+inline bool is_hadamard_op(const Op& op, int* q) {
+  if (op.kind != OP_PAIR || op.n_tgt != 1 || op.n_ctrl != 0) return false;
+  const double s = 1. / std::sqrt(2.);
+  if (!(op.m[0] == cplx(s, 0) && op.m[1] == cplx(s, 0) && op.m[2] == cplx(s, 0) && op.m[3] == cplx(-s, 0))) return false;
+  *q = op.tgt[0];
+  return true;
+}
+inline bool is_cphase_op(const Op& op, int a, int b, double theta) {
+  if (op.kind != OP_DIAG || op.n_tgt != 0 || op.n_ctrl != 2) return false;
+  if (!((op.ctrl[0] == a && op.ctrl[1] == b) || (op.ctrl[0] == b && op.ctrl[1] == a))) return false;
+  return op.m[0] == cplx(std::cos(theta), std::sin(theta));  // std::polar(1., theta), QuantumGate.h:262-265
+}
+inline bool is_swap_op(const Op& op, int a, int b) {
+  if (op.kind != OP_PAIR || op.n_tgt != 2 || op.n_ctrl != 0) return false;
+  if (!(op.m[0] == cplx(0, 0) && op.m[3] == cplx(0, 0) && op.m[1] == cplx(1, 0) && op.m[2] == cplx(1, 0))) return false;
+  return (op.tgt[0] == a && op.tgt[1] == b) || (op.tgt[0] == b && op.tgt[1] == a);
+}
+// swaps (sq,eq), (sq+1,eq-1) ... starting at ops[i]; returns ops consumed or -1
+inline int match_swaps(const std::vector<Op>& ops, size_t i, int sq, int eq) {
+  int used = 0;
+  for (int s = sq, e = eq; s < e; ++s, --e, ++used)
+    if (i + used >= ops.size() || !is_swap_op(ops[i + used], s, e)) return -1;
+  return used;
+}
+}  // namespace detail
+
+// Tries to match a QFT / IQFT of at least `min_qubits` qubits starting exactly at ops[i].
+inline QftMatch match_qft(const std::vector<Op>& ops, size_t i, int min_qubits = 4) {
+  using namespace detail;
+  QftMatch none;
+  const double pi_2 = 1.57079632679489661923;  // M_PI_2
+  const size_t N = ops.size();
+  int q0 = 0;
+  // ---- forward: H(eq) [CP(eq, eq-1 .. sq)] H(eq-1) ... H(sq) [swaps]
+  if (i < N && is_hadamard_op(ops[i], &q0)) {
+    const int eq = q0;
+    // the run of controlled phases after the first H fixes sq
+    size_t j = i + 1;
+    double phase = pi_2;
+    int ctrl = eq - 1;
+    while (j < N && ctrl >= 0 && is_cphase_op(ops[j], eq, ctrl, phase)) {
+      ++j;
+      --ctrl;
+      phase *= 0.5;
+    }
+    const int sq = ctrl + 1;
+    if (eq - sq + 1 >= min_qubits) {
+      bool ok = true;
+      size_t p = i + 1;
+      for (int cur = eq; cur > sq && ok; --cur) {
+        double ph = pi_2;
+        for (int c = cur - 1; c >= sq && ok; --c) {
+          ok = p < N && is_cphase_op(ops[p], cur, c, ph);
+          ++p;
+          ph *= 0.5;
+        }
+        int hq = -1;
+        ok = ok && p < N && is_hadamard_op(ops[p], &hq) && hq == cur - 1;
+        ++p;
+      }
+      if (ok) {
+        QftMatch m;
+        m.sq = sq;
+        m.eq = eq;
+        m.inverse = false;
+        const int sw = match_swaps(ops, p, sq, eq);
+        m.do_swap = sw > 0;
+        m.length = (int)(p - i) + (sw > 0 ? sw : 0);
+        return m;
+      }
+    }
+  }
+  // ---- inverse: [swaps] H(sq) CP(sq+1, sq) H(sq+1) CP(sq+2, sq+1) CP(sq+2, sq) ... H(eq)
+  {
+    size_t p = i;
+    int n_sw = 0, sw_s = -1, sw_e = -1;
+    // leading swaps, if any, fix (sq, eq)
+    if (p < N && ops[p].kind == OP_PAIR && ops[p].n_tgt == 2 && ops[p].n_ctrl == 0) {
+      sw_s = std::min(ops[p].tgt[0], ops[p].tgt[1]);
+      sw_e = std::max(ops[p].tgt[0], ops[p].tgt[1]);
+      const int used = match_swaps(ops, p, sw_s, sw_e);
+      if (used <= 0) return none;
+      n_sw = used;
+      p += used;
+    }
+    int sq = 0;
+    if (!(p < N && is_hadamard_op(ops[p], &sq))) return none;
+    if (n_sw && sq != sw_s) return none;
+    ++p;
+    int cur = sq + 1;
+    for (;;) {
+      // CP(cur, cur-1 .. sq) with phases -pi/2, -pi/4 ...
+      size_t pp = p;
+      double ph = -pi_2;
+      bool ok = true;
+      for (int c = cur - 1; c >= sq && ok; --c) {
+        ok = pp < N && is_cphase_op(ops[pp], cur, c, ph);
+        ++pp;
+        ph *= 0.5;
+      }
+      int hq = -1;
+      ok = ok && pp < N && is_hadamard_op(ops[pp], &hq) && hq == cur;
+      if (!ok) break;
+      p = pp + 1;
+      ++cur;
+    }
+    const int eq = cur - 1;
+    if (eq - sq + 1 < min_qubits) return none;
+    if (n_sw && eq != sw_e) return none;
+    QftMatch m;
+    m.sq = sq;
+    m.eq = eq;
+    m.inverse = true;
+    m.do_swap = n_sw > 0;
+    m.length = (int)(p - i);
+    return m;
+  }
 }
 
 }  // namespace qcsim

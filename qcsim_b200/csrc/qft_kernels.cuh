@@ -1,0 +1,334 @@
+// qft_kernels.cuh -- the quantum Fourier transform as radix-8 FFT passes, and bit-permutation passes.
+//
+// QuantumFourierTransform::QFT (QuantumFourierTransform.h:35-60) is, for every qubit `cur` from the
+// top down:  H(cur), then a controlled phase pi/2^(cur-ctrl) from every lower qubit ctrl.  The
+// controlled phases are diagonal, so for a GROUP of up to 3 adjacent qubits c2 > c1 > c0 all gates
+// with their target in the group reduce to
+//     [ H(c2) CP(c2,c1) CP(c2,c0) H(c1) CP(c1,c0) H(c0) ]   (a radix-8 butterfly on 8 amplitudes)
+//   x  amp(x2 x1 x0) *= P^(x2 + 2 x1 + 4 x0),   P = exp(i pi R / 2^c2),
+// where R is the value of ALL lower qubits of the amplitude's index (bits [sq, c0)): one sincospi
+// and 13 complex multiplies per 8 amplitudes instead of up to 3 x 30 controlled-phase passes.
+// This is exact algebra on the reference's gate sequence -- the same matrices (1/sqrt 2,
+// std::polar(1, pi/2), std::polar(1, pi/4) come from the host), only the diagonal factors are
+// multiplied together before they meet the amplitude; results agree with the gate-by-gate
+// reference to ~1e-15 (tests: 1e-12).
+//
+// One pass = one kernel over tiles, as in tile_kernels.cuh: tile = the low L index bits (contiguous
+// 2^L-amplitude runs in HBM) + the bits of up to 4 groups; each group is one round on the
+// shared-memory tile.  A 30-qubit QFT is 3 passes (10 rounds) instead of 465 gate passes.
+// IQFT (:62-87) is the adjoint: groups bottom-up, conjugate twiddle first, inverse butterfly after.
+// Bound: HBM (32 B per amplitude per pass; ~25 DFMA-class instructions per amplitude per round).
+#pragma once
+
+#include "common.cuh"
+
+namespace qcsim {
+
+constexpr int kMaxQftGroups = 4;
+
+struct QftGroup {
+  int size;         // 1..3 qubits
+  int lbit;         // tile-local bit of the group's lowest qubit (the others follow)
+  int top_qubit;    // logical index of the group's highest qubit (c2)
+  int pad;
+  uint32_t tb[3];   // tile bit walked by item-index bit j (byte each), for the k - size other bits
+  uint32_t pad2;
+};
+
+// logical value of the lower qubits = sum over segments ((phys >> from) & ((1 << len) - 1)) << to
+struct QftSegment {
+  int from, len, to, pad;
+};
+
+struct QftPassArgs {
+  int k;                 // tile bits
+  int low_identity;      // number of low tile bits that are the low index bits
+  int n_groups;
+  int inverse;
+  uint64_t n_tiles;
+  uint64_t rank_bits;    // physical index bits above the local slice (rank << n_local), 0 on one GPU
+  int tpos[kMaxTileBits];
+  int sq;                // lowest qubit of the transform: bits below it never enter R
+  int n_seg;
+  QftSegment seg[4];     // physical index -> logical value of the qubits (for R)
+  double s;              // 1/sqrt(2), HadamardGate (SimpleGates.h:588-596)
+  double2 ph2, ph4;      // std::polar(1., +-pi/2), std::polar(1., +-pi/4) (QuantumGate.h:262-265), sign by direction
+  QftGroup groups[kMaxQftGroups];
+};
+
+__device__ __forceinline__ void hadamard_pair(amp& a, amp& b, double s) {
+  const amp x = a, y = b;
+  a = make_amp(s * (x.x + y.x), s * (x.y + y.y));
+  b = make_amp(s * (x.x - y.x), s * (x.y - y.y));
+}
+
+template <int G>
+__device__ __forceinline__ void qft_group(amp (&v)[8], const QftPassArgs& A, bool inverse, amp P) {
+  constexpr int N = 1 << G;
+  // powers of the twiddle base: amp x gets P^rev(x)
+  amp pw[8];
+  pw[1] = P;
+  if (G >= 2) {
+    pw[2] = cmul(P, P);
+    pw[3] = cmul(pw[2], P);
+  }
+  if (G >= 3) {
+    pw[4] = cmul(pw[2], pw[2]);
+    pw[5] = cmul(pw[4], P);
+    pw[6] = cmul(pw[3], pw[3]);
+    pw[7] = cmul(pw[6], P);
+  }
+  auto twiddle = [&]() {
+#pragma unroll
+    for (int x = 1; x < N; ++x) {
+      int rev = 0;
+#pragma unroll
+      for (int b = 0; b < G; ++b)
+        if ((x >> b) & 1) rev |= 1 << (G - 1 - b);
+      v[x] = cmul(v[x], pw[rev]);
+    }
+  };
+  auto hadamard = [&](int bit) {
+#pragma unroll
+    for (int x = 0; x < N; ++x)
+      if (!((x >> bit) & 1)) hadamard_pair(v[x], v[x | (1 << bit)], A.s);
+  };
+  auto cphase = [&](int tbit, int cbit, amp ph) {
+#pragma unroll
+    for (int x = 0; x < N; ++x)
+      if (((x >> tbit) & 1) && ((x >> cbit) & 1)) v[x] = cmul(v[x], ph);
+  };
+  if (!inverse) {
+    if (G == 3) {
+      hadamard(2);
+      cphase(2, 1, A.ph2);
+      cphase(2, 0, A.ph4);
+      hadamard(1);
+      cphase(1, 0, A.ph2);
+      hadamard(0);
+    } else if (G == 2) {
+      hadamard(1);
+      cphase(1, 0, A.ph2);
+      hadamard(0);
+    } else {
+      hadamard(0);
+    }
+    twiddle();
+  } else {
+    twiddle();
+    if (G == 3) {
+      hadamard(0);
+      cphase(1, 0, A.ph2);
+      hadamard(1);
+      cphase(2, 1, A.ph2);
+      cphase(2, 0, A.ph4);
+      hadamard(2);
+    } else if (G == 2) {
+      hadamard(0);
+      cphase(1, 0, A.ph2);
+      hadamard(1);
+    } else {
+      hadamard(0);
+    }
+  }
+}
+
+static __global__ void __launch_bounds__(kTileThreads, 2) k_qft_pass(amp* __restrict__ psi, const __grid_constant__ QftPassArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  amp* tile = reinterpret_cast<amp*>(smem_raw);
+  const int k = A.k;
+  const uint32_t tile_amps = 1u << k;
+  const int L = A.low_identity;
+  const uint32_t low_mask = (1u << L) - 1u;
+  const uint32_t tid = threadIdx.x;
+  const bool inverse = A.inverse != 0;
+
+  const uint32_t loc_fixed = (tid << 1) & (tile_amps - 1u);
+  uint64_t g_fixed = loc_fixed & low_mask;
+#pragma unroll 1
+  for (int j = L; j < k; ++j) g_fixed |= (uint64_t)((loc_fixed >> j) & 1u) << A.tpos[j];
+  const uint32_t s_fixed = swz(loc_fixed);
+  const uint32_t n_it = (tile_amps >> 1) > kTileThreads ? (tile_amps >> 1) / kTileThreads : 1u;
+  const bool mover = (tid << 1) < tile_amps;
+
+  for (uint64_t t = blockIdx.x; t < A.n_tiles; t += gridDim.x) {
+    uint64_t gbase = t;
+#pragma unroll 1
+    for (int j = 0; j < k; ++j) gbase = insert_zero(gbase, A.tpos[j]);
+
+    if (mover) {
+#pragma unroll 1
+      for (uint32_t it0 = 0; it0 < n_it; it0 += 4) {  // 4 loads in flight per thread
+        amp2 x[4];
+#pragma unroll
+        for (uint32_t u = 0; u < 4; ++u) {
+          const uint32_t lv = (it0 + u) << 9;
+          uint64_t gv = 0;
+#pragma unroll 1
+          for (int j = 9; j < k; ++j) gv |= (uint64_t)((lv >> j) & 1u) << A.tpos[j];
+          if (it0 + u < n_it) x[u] = ld_amp2(psi + (gbase | g_fixed | gv));
+        }
+#pragma unroll
+        for (uint32_t u = 0; u < 4; ++u) {
+          if (it0 + u >= n_it) continue;
+          const uint32_t s = s_fixed ^ swz((it0 + u) << 9);
+          tile[s] = x[u].a;
+          tile[s ^ 1u] = x[u].b;
+        }
+      }
+    }
+    __syncthreads();
+
+#pragma unroll 1
+    for (int gi = 0; gi < A.n_groups; ++gi) {
+      const QftGroup grp = A.groups[gi];
+      const int G = grp.size;
+      const uint32_t items = tile_amps >> G;
+      const uint32_t so0 = swz(1u << grp.lbit), so1 = swz(2u << grp.lbit), so2 = swz(4u << grp.lbit);
+      // R = logical value of the qubits in [sq, lowest qubit of the group)
+      const int c0 = grp.top_qubit - G + 1;
+      const uint64_t r_mask = ((1ULL << c0) - 1ULL) & ~((1ULL << A.sq) - 1ULL);
+      const double scale = exp2(-(double)grp.top_qubit);  // exact power of two
+#pragma unroll 1
+      for (uint32_t item = tid; item < items; item += kTileThreads) {
+        uint32_t lbase = 0;
+#pragma unroll
+        for (int j = 0; j < 11; ++j) lbase |= ((item >> j) & 1u) << ((grp.tb[j >> 2] >> (8 * (j & 3))) & 31u);
+        // physical index of the item's amplitudes (group bits = 0) -> logical value of the lower qubits
+        uint64_t phys = gbase | A.rank_bits | (lbase & low_mask);
+#pragma unroll 1
+        for (int j = L; j < k; ++j) phys |= (uint64_t)((lbase >> j) & 1u) << A.tpos[j];
+        uint64_t logical = 0;
+#pragma unroll
+        for (int sgi = 0; sgi < 4; ++sgi)
+          if (sgi < A.n_seg) logical |= ((phys >> A.seg[sgi].from) & ((1ULL << A.seg[sgi].len) - 1ULL)) << A.seg[sgi].to;
+        const uint64_t R = logical & r_mask;
+        double sn, cs;
+        sincospi((double)R * scale, &sn, &cs);  // argument exact: R < 2^53, scale a power of two
+        const amp P = make_amp(cs, inverse ? -sn : sn);
+        const uint32_t sl = swz(lbase);
+        amp v[8];
+        if (G == 3) {
+#pragma unroll
+          for (int x = 0; x < 8; ++x) v[x] = tile[sl ^ ((x & 1) ? so0 : 0u) ^ ((x & 2) ? so1 : 0u) ^ ((x & 4) ? so2 : 0u)];
+          qft_group<3>(v, A, inverse, P);
+#pragma unroll
+          for (int x = 0; x < 8; ++x) tile[sl ^ ((x & 1) ? so0 : 0u) ^ ((x & 2) ? so1 : 0u) ^ ((x & 4) ? so2 : 0u)] = v[x];
+        } else if (G == 2) {
+#pragma unroll
+          for (int x = 0; x < 4; ++x) v[x] = tile[sl ^ ((x & 1) ? so0 : 0u) ^ ((x & 2) ? so1 : 0u)];
+          qft_group<2>(v, A, inverse, P);
+#pragma unroll
+          for (int x = 0; x < 4; ++x) tile[sl ^ ((x & 1) ? so0 : 0u) ^ ((x & 2) ? so1 : 0u)] = v[x];
+        } else {
+          v[0] = tile[sl];
+          v[1] = tile[sl ^ so0];
+          qft_group<1>(v, A, inverse, P);
+          tile[sl] = v[0];
+          tile[sl ^ so0] = v[1];
+        }
+      }
+      __syncthreads();
+    }
+
+    if (mover) {
+#pragma unroll 1
+      for (uint32_t it = 0; it < n_it; ++it) {
+        const uint32_t lv = it << 9;
+        uint64_t gv = 0;
+#pragma unroll 1
+        for (int j = 9; j < k; ++j) gv |= (uint64_t)((lv >> j) & 1u) << A.tpos[j];
+        const uint32_t s = s_fixed ^ swz(lv);
+        amp2 x;
+        x.a = tile[s];
+        x.b = tile[s ^ 1u];
+        st_amp2(psi + (gbase | g_fixed | gv), x);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---- in-tile bit permutation: one HBM pass for any permutation of <= 12 index bits ------------------
+// Used for the QFT's qubit reversal (QubitsSwapper.h:23-34: SWAP(s,e), SWAP(s+1,e-1) ...) and for
+// putting a sharded register back into canonical qubit order.  The tile is loaded as in the gate
+// passes; on the way out, output slot j receives the amplitude from slot src(j), where src permutes
+// the bits of j.
+struct PermPassArgs {
+  int k;
+  int low_identity;
+  uint64_t n_tiles;
+  int tpos[kMaxTileBits];
+  int src_bit[kMaxTileBits];  // output local bit j is taken from input local bit src_bit[j]
+};
+
+static __global__ void __launch_bounds__(kTileThreads, 2) k_tile_permute(amp* __restrict__ psi, const __grid_constant__ PermPassArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  amp* tile = reinterpret_cast<amp*>(smem_raw);
+  const int k = A.k;
+  const uint32_t tile_amps = 1u << k;
+  const int L = A.low_identity;
+  const uint32_t low_mask = (1u << L) - 1u;
+  const uint32_t tid = threadIdx.x;
+  const uint32_t loc_fixed = (tid << 1) & (tile_amps - 1u);
+  uint64_t g_fixed = loc_fixed & low_mask;
+#pragma unroll 1
+  for (int j = L; j < k; ++j) g_fixed |= (uint64_t)((loc_fixed >> j) & 1u) << A.tpos[j];
+  const uint32_t s_fixed = swz(loc_fixed);
+  const uint32_t n_it = (tile_amps >> 1) > kTileThreads ? (tile_amps >> 1) / kTileThreads : 1u;
+  const bool mover = (tid << 1) < tile_amps;
+  // input slots of this thread's two output amplitudes per iteration: src() is linear over XOR
+  auto src = [&](uint32_t j) {
+    uint32_t o = 0;
+#pragma unroll 1
+    for (int b = 0; b < k; ++b) o |= ((j >> b) & 1u) << A.src_bit[b];
+    return o;
+  };
+  const uint32_t src_fixed = swz(src(loc_fixed));
+  const uint32_t src_one = swz(src(1u));
+
+  for (uint64_t t = blockIdx.x; t < A.n_tiles; t += gridDim.x) {
+    uint64_t gbase = t;
+#pragma unroll 1
+    for (int j = 0; j < k; ++j) gbase = insert_zero(gbase, A.tpos[j]);
+    if (mover) {
+#pragma unroll 1
+      for (uint32_t it0 = 0; it0 < n_it; it0 += 4) {
+        amp2 x[4];
+#pragma unroll
+        for (uint32_t u = 0; u < 4; ++u) {
+          const uint32_t lv = (it0 + u) << 9;
+          uint64_t gv = 0;
+#pragma unroll 1
+          for (int j = 9; j < k; ++j) gv |= (uint64_t)((lv >> j) & 1u) << A.tpos[j];
+          if (it0 + u < n_it) x[u] = ld_amp2(psi + (gbase | g_fixed | gv));
+        }
+#pragma unroll
+        for (uint32_t u = 0; u < 4; ++u) {
+          if (it0 + u >= n_it) continue;
+          const uint32_t s = s_fixed ^ swz((it0 + u) << 9);
+          tile[s] = x[u].a;
+          tile[s ^ 1u] = x[u].b;
+        }
+      }
+    }
+    __syncthreads();
+    if (mover) {
+#pragma unroll 1
+      for (uint32_t it = 0; it < n_it; ++it) {
+        const uint32_t lv = it << 9;
+        uint64_t gv = 0;
+#pragma unroll 1
+        for (int j = 9; j < k; ++j) gv |= (uint64_t)((lv >> j) & 1u) << A.tpos[j];
+        const uint32_t s = src_fixed ^ swz(src(lv));
+        amp2 x;
+        x.a = tile[s];
+        x.b = tile[s ^ src_one];
+        st_amp2(psi + (gbase | g_fixed | gv), x);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace qcsim

@@ -27,10 +27,8 @@
 
 namespace qcsim {
 
-constexpr int kMaxTileBits = 12;   // 2^12 x 16 B = 64 KiB of shared memory per tile
 constexpr int kRoundBits = 3;      // amplitudes per thread per round = 2^3
 constexpr int kMaxVariantBits = 2; // matrices per round <= 2^2
-constexpr int kTileThreads = 256;
 constexpr int kMaxTileRounds = 7;  // per launch: 7 rounds x 4 matrices x 1 KiB fits the 32 KiB parameter block
 constexpr int kMaxTileMats = 28;
 constexpr int kRoundMatAmps = 64;  // one 8x8 complex matrix
@@ -54,11 +52,6 @@ struct TilePassArgs {
   double2 mats[kMaxTileMats * kRoundMatAmps];  // round matrices, row-major 8x8, variant-major per round
 };
 static_assert(sizeof(TilePassArgs) <= 32764, "kernel parameter block limit");
-
-// 16-byte slot swizzle, linear over XOR: folds every 3-bit group of the index onto the low 3
-// bits, so any 8 indices that differ in 3 bits with distinct (position mod 3) hit 8 distinct
-// 16-byte bank groups.  The host picks which tile bits the low 3 item-index bits walk over.
-__host__ __device__ __forceinline__ uint32_t swz(uint32_t j) { return j ^ ((j >> 3) & 7u) ^ ((j >> 6) & 7u) ^ ((j >> 9) & 7u); }
 
 // acc += m * a as four fused multiply-adds (the mat-vec of a round is fp64-pipe bound: 32 DFMA
 // per amplitude; the unfused kernels keep the reference's separately rounded products instead)

@@ -99,3 +99,18 @@ int hl_dist_plan(const qcsim_gate* gates, int count, int n, int n_local, int ran
   return (int)steps.size();
 }
 }
+
+// ---- QFT stream recognition (planner.h: match_qft) ----------------------------------------------
+extern "C" {
+// out = {length, sq, eq, do_swap, inverse}
+void hl_match_qft(const qcsim_gate* gates, int count, int start, int min_qubits, int* out) {
+  std::vector<Op> ops;
+  for (int i = 0; i < count; ++i) ops.push_back(classify(gates[i].nq, gates[i].m, gates[i].flags, gates[i].q, gates[i].c1, gates[i].c2));
+  const QftMatch m = match_qft(ops, (size_t)start, min_qubits);
+  out[0] = m.length;
+  out[1] = m.sq;
+  out[2] = m.eq;
+  out[3] = m.do_swap ? 1 : 0;
+  out[4] = m.inverse ? 1 : 0;
+}
+}

@@ -169,3 +169,37 @@ def test_planner_preserves_semantics_and_fuses(hl, n, K, L):
     for i in flat:
         b = apply_op(b, ops[i], n)
     assert np.max(np.abs(a - b)) < 1e-13
+
+
+def _match(hl, circ, start=0, min_qubits=4):
+    out = (C.c_int * 5)()
+    hl.hl_match_qft(pack(circ), len(circ), start, min_qubits, out)
+    return list(out)
+
+
+@pytest.mark.parametrize("n,sq,eq", [(8, 0, 7), (10, 2, 8), (6, 1, 4)])
+@pytest.mark.parametrize("swap", [True, False])
+@pytest.mark.parametrize("inverse", [False, True])
+def test_qft_stream_recognition(hl, n, sq, eq, swap, inverse):
+    """the gate stream QCSim's QuantumFourierTransform emits (QuantumFourierTransform.h:35-87) is
+    recognised exactly -- range, direction, swap -- and nothing else is"""
+    circ = circuits.qft_circuit(n, sq, eq, swap, inverse)
+    assert _match(hl, circ) == [len(circ), sq, eq, int(swap), int(inverse)]
+    # embedded after other gates: found at its offset, not before
+    pre = [(gates.RxGate(0.3), 0, 0, 0), (gates.CNOTGate(), 1, 0, 0)]
+    assert _match(hl, pre + circ, start=len(pre))[0] == len(circ)
+    assert _match(hl, pre + circ, start=0)[0] == 0
+    # one phase off by an ulp-scale amount, or one gate missing: no match of the full transform
+    broken = list(circ)
+    k = next(i for i, g in enumerate(broken) if g[0].name.startswith("cp"))
+    broken[k] = (gates.ControlledPhaseShiftGate(0.123), *broken[k][1:])
+    got = _match(hl, broken)
+    assert got[0] != len(circ)
+
+
+
+def test_qft_recognition_ignores_short_and_foreign_streams(hl):
+    assert _match(hl, circuits.qft_circuit(5, 0, 2))[0] == 0          # below min_qubits
+    assert _match(hl, circuits.random_circuit(8, 2, seed=3))[0] == 0
+    h = (gates.HadamardGate(), 3, 0, 0)
+    assert _match(hl, [h, h, h, h, h])[0] == 0
