@@ -482,7 +482,7 @@ int engine_qft_passes(qcsim_sv* h, int sq, int eq, bool inverse, uint64_t rank_b
   }
   static bool attr_set = false;
   if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(k_qft_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(k_qft_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(k_tile_permute, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     attr_set = true;
   }
@@ -518,7 +518,7 @@ int engine_qft_passes(qcsim_sv* h, int sq, int eq, bool inverse, uint64_t rank_b
       const uint32_t reg_mask = ((1u << G.size) - 1u) << lbit;
       item_bit_order(k, reg_mask, G.tb, 3);
     }
-    const size_t smem = sizeof(amp) << k;
+    const size_t smem = (sizeof(amp) << k) + sizeof(amp) * ((k == 12 ? kMaxQftGroups * kQftItems3 : 0) + kMaxQftGroups);
     const uint64_t grid = std::min<uint64_t>(A.n_tiles, (uint64_t)kNumSMs * 2);
     k_qft_pass<<<(unsigned)grid, kTileThreads, smem, h->stream>>>(h->psi, A);
     CUDA_TRY(cudaGetLastError());
@@ -585,7 +585,7 @@ int engine_permute_bits(qcsim_sv* h, const int* src_of) {
     A.n_tiles = 1ULL << (nl - k);
     for (int j = 0; j < kMaxTileBits; ++j) A.src_bit[j] = j < k ? local_of[perm[A.tpos[j]]] : j;
     const size_t smem = sizeof(amp) << k;
-    const uint64_t grid = std::min<uint64_t>(A.n_tiles, (uint64_t)kNumSMs * 2);
+    const uint64_t grid = std::min<uint64_t>(A.n_tiles, (uint64_t)kNumSMs * 3);
     k_tile_permute<<<(unsigned)grid, kTileThreads, smem, h->stream>>>(h->psi, A);
     CUDA_TRY(cudaGetLastError());
     count_pass(h, h->dim_local);

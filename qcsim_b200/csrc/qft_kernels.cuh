@@ -133,15 +133,47 @@ __device__ __forceinline__ void qft_group(amp (&v)[8], const QftPassArgs& A, boo
   }
 }
 
+// Shared memory: tile (2^k amps) | per-item thread-part twiddles of the 3-qubit groups
+// (kMaxQftGroups x 512 amps, only when k == 12) | per-tile CTA-part twiddles (kMaxQftGroups amps).
+constexpr int kQftItems3 = 512;  // items of a 3-qubit group in a 12-bit tile
+
+__device__ __forceinline__ uint64_t qft_logical(const QftPassArgs& A, uint64_t phys) {
+  uint64_t logical = 0;
+#pragma unroll
+  for (int sgi = 0; sgi < 4; ++sgi)
+    if (sgi < A.n_seg) logical |= ((phys >> A.seg[sgi].from) & ((1ULL << A.seg[sgi].len) - 1ULL)) << A.seg[sgi].to;
+  return logical;
+}
+
+__device__ __forceinline__ uint32_t qft_lbase(const QftGroup& grp, uint32_t item) {
+  uint32_t lbase = 0;
+#pragma unroll
+  for (int j = 0; j < 11; ++j) lbase |= ((item >> j) & 1u) << ((grp.tb[j >> 2] >> (8 * (j & 3))) & 31u);
+  return lbase;
+}
+
+// twiddle base exp(+-i pi R / 2^top) for the lower-qubit value R (masked to [sq, c0))
+__device__ __forceinline__ amp qft_base(const QftPassArgs& A, const QftGroup& grp, uint64_t logical, bool inverse) {
+  const int c0 = grp.top_qubit - grp.size + 1;
+  const uint64_t r_mask = ((1ULL << c0) - 1ULL) & ~((1ULL << A.sq) - 1ULL);
+  const uint64_t R = logical & r_mask;
+  double sn, cs;
+  sincospi((double)R * exp2(-(double)grp.top_qubit), &sn, &cs);  // exact argument: R < 2^53, scale a power of two
+  return make_amp(cs, inverse ? -sn : sn);
+}
+
 static __global__ void __launch_bounds__(kTileThreads, 2) k_qft_pass(amp* __restrict__ psi, const __grid_constant__ QftPassArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   amp* tile = reinterpret_cast<amp*>(smem_raw);
   const int k = A.k;
   const uint32_t tile_amps = 1u << k;
+  amp* tw_item = tile + tile_amps;                              // [group][item], k == 12 only
+  amp* tw_cta = tw_item + (k == 12 ? kMaxQftGroups * kQftItems3 : 0);  // [group]
   const int L = A.low_identity;
   const uint32_t low_mask = (1u << L) - 1u;
   const uint32_t tid = threadIdx.x;
   const bool inverse = A.inverse != 0;
+  const bool tabled = (k == 12);
 
   const uint32_t loc_fixed = (tid << 1) & (tile_amps - 1u);
   uint64_t g_fixed = loc_fixed & low_mask;
@@ -151,17 +183,44 @@ static __global__ void __launch_bounds__(kTileThreads, 2) k_qft_pass(amp* __rest
   const uint32_t n_it = (tile_amps >> 1) > kTileThreads ? (tile_amps >> 1) / kTileThreads : 1u;
   const bool mover = (tid << 1) < tile_amps;
 
+  // thread-part twiddles: depend on the item's tile bits only, so once per kernel
+  if (tabled) {
+#pragma unroll 1
+    for (int gi = 0; gi < A.n_groups; ++gi) {
+      const QftGroup grp = A.groups[gi];
+      if (grp.size != 3) continue;
+#pragma unroll 1
+      for (uint32_t item = tid; item < kQftItems3; item += kTileThreads) {
+        const uint32_t lbase = qft_lbase(grp, item);
+        uint64_t phys = lbase & low_mask;
+#pragma unroll 1
+        for (int j = L; j < k; ++j) phys |= (uint64_t)((lbase >> j) & 1u) << A.tpos[j];
+        tw_item[gi * kQftItems3 + item] = qft_base(A, grp, qft_logical(A, phys), inverse);
+      }
+    }
+  }
+
+  // swizzled tile offsets (in bytes) of this thread's two items per 3-qubit group: once per kernel
+  uint32_t slb[kMaxQftGroups][2];
+#pragma unroll
+  for (int gi = 0; gi < kMaxQftGroups; ++gi)
+#pragma unroll
+    for (int it = 0; it < 2; ++it) slb[gi][it] = (tabled && gi < A.n_groups) ? (swz(qft_lbase(A.groups[gi], tid + it * kTileThreads)) << 4) : 0u;
+  unsigned char* const tile_bytes = smem_raw;
+
   for (uint64_t t = blockIdx.x; t < A.n_tiles; t += gridDim.x) {
     uint64_t gbase = t;
 #pragma unroll 1
     for (int j = 0; j < k; ++j) gbase = insert_zero(gbase, A.tpos[j]);
+    // CTA-part twiddles of this tile (bits outside the tile + rank bits)
+    if (tid < (uint32_t)A.n_groups) tw_cta[tid] = qft_base(A, A.groups[tid], qft_logical(A, gbase | A.rank_bits), inverse);
 
     if (mover) {
 #pragma unroll 1
-      for (uint32_t it0 = 0; it0 < n_it; it0 += 4) {  // 4 loads in flight per thread
-        amp2 x[4];
+      for (uint32_t it0 = 0; it0 < n_it; it0 += 8) {  // 8 loads in flight per thread
+        amp2 x[8];
 #pragma unroll
-        for (uint32_t u = 0; u < 4; ++u) {
+        for (uint32_t u = 0; u < 8; ++u) {
           const uint32_t lv = (it0 + u) << 9;
           uint64_t gv = 0;
 #pragma unroll 1
@@ -169,7 +228,7 @@ static __global__ void __launch_bounds__(kTileThreads, 2) k_qft_pass(amp* __rest
           if (it0 + u < n_it) x[u] = ld_amp2(psi + (gbase | g_fixed | gv));
         }
 #pragma unroll
-        for (uint32_t u = 0; u < 4; ++u) {
+        for (uint32_t u = 0; u < 8; ++u) {
           if (it0 + u >= n_it) continue;
           const uint32_t s = s_fixed ^ swz((it0 + u) << 9);
           tile[s] = x[u].a;
@@ -179,33 +238,40 @@ static __global__ void __launch_bounds__(kTileThreads, 2) k_qft_pass(amp* __rest
     }
     __syncthreads();
 
-#pragma unroll 1
-    for (int gi = 0; gi < A.n_groups; ++gi) {
+#pragma unroll
+    for (int gi = 0; gi < kMaxQftGroups; ++gi) {
+      if (gi >= A.n_groups) break;
       const QftGroup grp = A.groups[gi];
       const int G = grp.size;
       const uint32_t items = tile_amps >> G;
       const uint32_t so0 = swz(1u << grp.lbit), so1 = swz(2u << grp.lbit), so2 = swz(4u << grp.lbit);
-      // R = logical value of the qubits in [sq, lowest qubit of the group)
-      const int c0 = grp.top_qubit - G + 1;
-      const uint64_t r_mask = ((1ULL << c0) - 1ULL) & ~((1ULL << A.sq) - 1ULL);
-      const double scale = exp2(-(double)grp.top_qubit);  // exact power of two
+      const amp p_cta = tw_cta[gi];
+      if (tabled && G == 3) {
+        // fast path (12-bit tile, 3-qubit group): two items per thread, addresses and the thread part
+        // of the twiddle precomputed; per amplitude one XOR + LDS + STS around the butterfly
+        uint32_t cb[8];
+#pragma unroll
+        for (int x = 0; x < 8; ++x) cb[x] = (((x & 1) ? so0 : 0u) ^ ((x & 2) ? so1 : 0u) ^ ((x & 4) ? so2 : 0u)) << 4;
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+          const amp P = cmul(p_cta, tw_item[gi * kQftItems3 + tid + it * kTileThreads]);
+          amp v[8];
+#pragma unroll
+          for (int x = 0; x < 8; ++x) v[x] = *reinterpret_cast<const amp*>(tile_bytes + (slb[gi][it] ^ cb[x]));
+          qft_group<3>(v, A, inverse, P);
+#pragma unroll
+          for (int x = 0; x < 8; ++x) *reinterpret_cast<amp*>(tile_bytes + (slb[gi][it] ^ cb[x])) = v[x];
+        }
+        __syncthreads();
+        continue;
+      }
 #pragma unroll 1
       for (uint32_t item = tid; item < items; item += kTileThreads) {
-        uint32_t lbase = 0;
-#pragma unroll
-        for (int j = 0; j < 11; ++j) lbase |= ((item >> j) & 1u) << ((grp.tb[j >> 2] >> (8 * (j & 3))) & 31u);
-        // physical index of the item's amplitudes (group bits = 0) -> logical value of the lower qubits
+        const uint32_t lbase = qft_lbase(grp, item);
         uint64_t phys = gbase | A.rank_bits | (lbase & low_mask);
 #pragma unroll 1
         for (int j = L; j < k; ++j) phys |= (uint64_t)((lbase >> j) & 1u) << A.tpos[j];
-        uint64_t logical = 0;
-#pragma unroll
-        for (int sgi = 0; sgi < 4; ++sgi)
-          if (sgi < A.n_seg) logical |= ((phys >> A.seg[sgi].from) & ((1ULL << A.seg[sgi].len) - 1ULL)) << A.seg[sgi].to;
-        const uint64_t R = logical & r_mask;
-        double sn, cs;
-        sincospi((double)R * scale, &sn, &cs);  // argument exact: R < 2^53, scale a power of two
-        const amp P = make_amp(cs, inverse ? -sn : sn);
+        const amp P = qft_base(A, grp, qft_logical(A, phys), inverse);
         const uint32_t sl = swz(lbase);
         amp v[8];
         if (G == 3) {
@@ -262,7 +328,7 @@ struct PermPassArgs {
   int src_bit[kMaxTileBits];  // output local bit j is taken from input local bit src_bit[j]
 };
 
-static __global__ void __launch_bounds__(kTileThreads, 2) k_tile_permute(amp* __restrict__ psi, const __grid_constant__ PermPassArgs A) {
+static __global__ void __launch_bounds__(kTileThreads, 3) k_tile_permute(amp* __restrict__ psi, const __grid_constant__ PermPassArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   amp* tile = reinterpret_cast<amp*>(smem_raw);
   const int k = A.k;
@@ -293,10 +359,10 @@ static __global__ void __launch_bounds__(kTileThreads, 2) k_tile_permute(amp* __
     for (int j = 0; j < k; ++j) gbase = insert_zero(gbase, A.tpos[j]);
     if (mover) {
 #pragma unroll 1
-      for (uint32_t it0 = 0; it0 < n_it; it0 += 4) {
-        amp2 x[4];
+      for (uint32_t it0 = 0; it0 < n_it; it0 += 8) {
+        amp2 x[8];
 #pragma unroll
-        for (uint32_t u = 0; u < 4; ++u) {
+        for (uint32_t u = 0; u < 8; ++u) {
           const uint32_t lv = (it0 + u) << 9;
           uint64_t gv = 0;
 #pragma unroll 1
@@ -304,7 +370,7 @@ static __global__ void __launch_bounds__(kTileThreads, 2) k_tile_permute(amp* __
           if (it0 + u < n_it) x[u] = ld_amp2(psi + (gbase | g_fixed | gv));
         }
 #pragma unroll
-        for (uint32_t u = 0; u < 4; ++u) {
+        for (uint32_t u = 0; u < 8; ++u) {
           if (it0 + u >= n_it) continue;
           const uint32_t s = s_fixed ^ swz((it0 + u) << 9);
           tile[s] = x[u].a;
