@@ -315,8 +315,10 @@ static int do_exchange(qcsim_sv* h, const DistStep& ex) {
   if (d->p2p) {
     SwapArgs A;
     std::memset(&A, 0, sizeof A);
-    for (int t = 0; t < n_sub; ++t) {
-      if (t == a) continue;
+    // peers in XOR order: in step d every rank of the group talks to rank ^ d -- a perfect
+    // matching, so no rank is the target of everybody at once
+    for (int dd = 1; dd < n_sub; ++dd) {
+      const int t = a ^ dd;
       const int peer = peer_of(t);
       const int j = A.n_peers++;
       A.remote[j] = d->peer_psi[peer] + (uint64_t)a * blk;  // the peer trades its block `a` for my block `t`

@@ -14,7 +14,12 @@ g = world.bit_length() - 1
 for rep in range(3):
     reg.reset_stats()
     torch.cuda.synchronize(); dist.barrier(); t0 = time.time()
+    multi = len(sys.argv) > 2 and sys.argv[2] == "multi"
     for i in range(4):
+        if multi:   # all global qubits in one batch -> one k = log2(world) exchange (all-to-all), and back
+            reg.ApplyGates([(H, q, 0, 0) for q in range(n - g, n)])
+            reg.ApplyGates([(H, n - g - 1 - q, 0, 0) for q in range(0, g)])
+            continue
         for q in range(n - g, n):
             reg.ApplyGate(H, q)
         for q in range(0, g):
