@@ -109,13 +109,17 @@ static int launch_pass(qcsim_sv* h, const std::vector<Op>& all, const PassPlan& 
   A.low_identity = L;
   A.n_tiles = 1ULL << (h->n_local - k);
   for (int j = 0; j < kMaxTileBits; ++j) A.tpos[j] = j < k ? plan.tile[j] : 0;
-  const size_t smem = (size_t)sizeof(amp) << k;
+  static const int want_pipe = env_int("QCSIM_TILE_PIPE", 0);
+  const bool pipe = want_pipe && (k == kMaxTileBits);  // double-buffered tiles, one CTA per SM
+  A.pipelined = pipe ? 1 : 0;
+  const size_t tile_smem = ((size_t)sizeof(amp) << k) * (pipe ? 2 : 1);
+  const size_t smem_max = tile_smem + (size_t)kMaxTileMats * kRoundMatAmps * sizeof(amp);
   static bool attr_set = false;
   if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(k_tile_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(k_tile_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (128 + 28) * 1024));
     attr_set = true;
   }
-  const int per_sm = std::max(1, std::min(2, (int)((220 * 1024) / (smem + 1024))));
+  const int per_sm = pipe ? 1 : std::max(1, std::min(2, (int)((220 * 1024) / (smem_max + 1024))));
   const uint64_t grid = std::min<uint64_t>(A.n_tiles, (uint64_t)kNumSMs * per_sm);
   static const int debug = env_int("QCSIM_DEBUG_PLAN", 0);
 
@@ -159,6 +163,8 @@ static int launch_pass(qcsim_sv* h, const std::vector<Op>& all, const PassPlan& 
       ++r;
     }
     A.n_rounds = n_rounds;
+    A.n_mats = (int)mat_index;
+    const size_t smem = tile_smem + mat_index * kRoundMatAmps * sizeof(amp);
     k_tile_pass<<<(unsigned)grid, kTileThreads, smem, h->stream>>>(h->psi, A);
     CUDA_TRY(cudaGetLastError());
     h->stats.kernel_launches += 1;

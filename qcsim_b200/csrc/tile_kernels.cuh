@@ -45,7 +45,9 @@ struct TilePassArgs {
   int k;                        // tile bits
   int n_rounds;
   int low_identity;             // L: number of low tile bits that are the low global bits
-  int pad0;
+  int n_mats;                   // matrices used by this launch
+  int pipelined;                // 1: double-buffered cp.async tile pipeline (one CTA per SM), 12-bit tiles only
+  int pad1;
   uint64_t n_tiles;
   int tpos[kMaxTileBits];       // global bit position of tile bit j (ascending, tpos[j] == j for j < L)
   TileRoundDesc rounds[kMaxTileRounds];
@@ -63,7 +65,20 @@ __device__ __forceinline__ amp cfma(amp m, amp a, amp acc) {
   return acc;
 }
 
-// Dynamic shared memory: 2^k amps (tile, swizzled).
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Dynamic shared memory: tile buffer(s) of 2^k amps (swizzled) | round matrices.  Default: two CTAs
+// per SM, each with one tile buffer (one loads/stores while the other computes).  Optional
+// (QCSIM_TILE_PIPE=1, 12-bit tiles): one CTA per SM with TWO tile buffers, the next tile streaming in
+// with cp.async while the rounds of the current one run -- measured slightly slower on B200 in
+// round 1 (39.5 vs 36.8 ms per 30-qubit layer: 8 warps per SM do not cover the LDS latency of the
+// matrix loads), kept for the next round's tuning.
 __global__ void __launch_bounds__(kTileThreads, 2) k_tile_pass(amp* __restrict__ psi, const __grid_constant__ TilePassArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   amp* tile = reinterpret_cast<amp*>(smem_raw);
@@ -73,6 +88,16 @@ __global__ void __launch_bounds__(kTileThreads, 2) k_tile_pass(amp* __restrict__
   const uint32_t low_mask = (1u << L) - 1u;
   const uint32_t items = tile_amps >> kRoundBits;
   const uint32_t tid = threadIdx.x;
+
+  // the launch's round matrices: parameter block -> shared memory, once per CTA.  A matrix entry is
+  // then one uniform-address LDS.128 (a broadcast, one wavefront) instead of two indexed constant
+  // loads: the indexed-constant cache saturates at half the fp64 rate of this kernel (ncu: IDC 50 %
+  // busy at fp64 47 %).
+  const bool pipe = (k == kMaxTileBits) && A.pipelined;
+  amp* const buf0 = tile;
+  amp* const buf1 = pipe ? tile + tile_amps : tile;
+  amp* const smats = tile + (pipe ? 2u : 1u) * tile_amps;
+  for (uint32_t i = tid; i < (uint32_t)A.n_mats * kRoundMatAmps; i += kTileThreads) smats[i] = A.mats[i];
 
   // global/shared offsets of this thread's amplitude pairs in the load/store phases: iteration
   // `it` handles local index loc = 2 * (tid + 256 * it); the tid part is fixed for the kernel
@@ -84,15 +109,42 @@ __global__ void __launch_bounds__(kTileThreads, 2) k_tile_pass(amp* __restrict__
   const uint32_t n_it = (tile_amps >> 1) > kTileThreads ? (tile_amps >> 1) / kTileThreads : 1u;
   const bool mover = (tid << 1) < tile_amps;
 
-  for (uint64_t t = blockIdx.x; t < A.n_tiles; t += gridDim.x) {
-    // global base of this tile: scatter t into the non-tile bit positions
-    uint64_t gbase = t;
+  auto gbase_of = [&](uint64_t t) {  // scatter t into the non-tile bit positions
+    uint64_t g = t;
 #pragma unroll 1
-    for (int j = 0; j < k; ++j) gbase = insert_zero(gbase, A.tpos[j]);
+    for (int j = 0; j < k; ++j) g = insert_zero(g, A.tpos[j]);
+    return g;
+  };
+  auto prefetch = [&](uint64_t t, amp* dst) {  // k == 12: 8 x 32 B per thread, asynchronous
+    const uint64_t gb = gbase_of(t);
+#pragma unroll
+    for (uint32_t it = 0; it < 8; ++it) {
+      const uint64_t gv = ((uint64_t)(it & 1u) << A.tpos[9]) | ((uint64_t)((it >> 1) & 1u) << A.tpos[10]) | ((uint64_t)((it >> 2) & 1u) << A.tpos[11]);
+      const amp* src = psi + (gb | g_fixed | gv);
+      const uint32_t s = s_fixed ^ swz(it << 9);
+      cp_async16(dst + s, src);
+      cp_async16(dst + (s ^ 1u), src + 1);
+    }
+  };
+  if (pipe) {
+    if (blockIdx.x < A.n_tiles) prefetch(blockIdx.x, buf0);
+    cp_async_commit();
+  }
+  uint32_t cur = 0;
 
-    // ---- HBM -> shared: each thread moves 2 adjacent amplitudes per 256-bit load; at K = 12 all
-    // eight loads of a thread are in flight together (64 KiB per CTA)
-    if (mover) {
+  for (uint64_t t = blockIdx.x; t < A.n_tiles; t += gridDim.x) {
+    tile = cur ? buf1 : buf0;
+    const uint64_t gbase = gbase_of(t);
+
+    if (pipe) {
+      // ---- the next tile starts streaming in; wait for this one only
+      const uint64_t nt = t + gridDim.x;
+      if (nt < A.n_tiles) prefetch(nt, cur ? buf0 : buf1);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else if (mover) {
+      // ---- HBM -> shared: each thread moves 2 adjacent amplitudes per 256-bit load; at K = 12 all
+      // eight loads of a thread are in flight together (64 KiB per CTA)
       if (n_it == 8) {
         amp2 x[8];
 #pragma unroll
@@ -160,7 +212,7 @@ __global__ void __launch_bounds__(kTileThreads, 2) k_tile_pass(amp* __restrict__
 #pragma unroll 1
         for (uint32_t a = 0; a < n_var; ++a) {
           if (!valid || vidx != a) continue;
-          const double2* __restrict__ M = A.mats + (size_t)(rd.mat_off + a) * kRoundMatAmps;
+          const amp* __restrict__ M = smats + (size_t)(rd.mat_off + a) * kRoundMatAmps;
 #pragma unroll
           for (int row = 0; row < 8; row += 2) {  // two rows x two items = 8 independent DFMA chains
             const amp ma = M[row * 8], mb = M[row * 8 + 8];
@@ -214,7 +266,9 @@ __global__ void __launch_bounds__(kTileThreads, 2) k_tile_pass(amp* __restrict__
       }
     }
     __syncthreads();
+    if (pipe) cur ^= 1u;
   }
+  if (pipe) cp_async_wait<0>();
 }
 
 }  // namespace qcsim
