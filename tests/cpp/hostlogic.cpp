@@ -114,3 +114,32 @@ void hl_match_qft(const qcsim_gate* gates, int count, int start, int min_qubits,
   out[4] = m.inverse ? 1 : 0;
 }
 }
+
+// ---- rounds of a fused pass (planner.h: schedule_rounds) -----------------------------------------
+extern "C" {
+// Plans `count` gates as ONE pass over the tile qubits in `tile_mask` and schedules its rounds.
+// Per round: rbits (3 ints, tile-local), n_var + vq (3 ints), n_ops; op indices appended to `order`.
+// Returns the number of rounds.
+int hl_rounds(const qcsim_gate* gates, int count, unsigned long long tile_mask, int max_var, int* rbits, int* nvar, int* vq,
+              int* nops, int* order, int* item_bits) {
+  std::vector<Op> ops;
+  PassPlan plan;
+  for (int q = 0; q < 64; ++q)
+    if ((tile_mask >> q) & 1ULL) plan.tile.push_back(q);
+  for (int i = 0; i < count; ++i) {
+    ops.push_back(classify(gates[i].nq, gates[i].m, gates[i].flags, gates[i].q, gates[i].c1, gates[i].c2));
+    if (ops.back().kind != OP_NOP) plan.ops.push_back(i);
+  }
+  const std::vector<RoundPlan> rounds = schedule_rounds(ops, plan, max_var);
+  int o = 0;
+  for (size_t r = 0; r < rounds.size(); ++r) {
+    for (int j = 0; j < 3; ++j) rbits[3 * r + j] = rounds[r].rbits[j];
+    nvar[r] = (int)rounds[r].vq.size();
+    for (int j = 0; j < 3; ++j) vq[3 * r + j] = j < nvar[r] ? rounds[r].vq[j] : -1;
+    for (int j = 0; j < 9; ++j) item_bits[9 * r + j] = rounds[r].item_bit[j];
+    nops[r] = (int)rounds[r].ops.size();
+    for (int i : rounds[r].ops) order[o++] = i;
+  }
+  return (int)rounds.size();
+}
+}

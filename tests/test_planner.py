@@ -203,3 +203,53 @@ def test_qft_recognition_ignores_short_and_foreign_streams(hl):
     assert _match(hl, circuits.random_circuit(8, 2, seed=3))[0] == 0
     h = (gates.HadamardGate(), 3, 0, 0)
     assert _match(hl, [h, h, h, h, h])[0] == 0
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_round_scheduler_invariants(hl, seed):
+    """schedule_rounds: every op lands in exactly one round whose 3 register bits hold its
+    non-diagonal targets and whose <= 2 variant qubits + register bits hold everything it merely
+    looks at; executing round by round equals program order; the item-index bit map is a bijection
+    onto the non-round tile bits with conflict-free low lanes."""
+    n, K = 12, 12
+    circ = [g for g in circuits.random_circuit(n, 3, seed=seed)] + circuits.ncnot_circuit([0, 1, 2, 3], 4, 5)
+    N = len(circ)
+    arr = pack(circ)
+    ops = (HlOp * N)()
+    for i in range(N):
+        hl.hl_classify(C.byref(arr, i * C.sizeof(_lib.GateStruct)), C.byref(ops[i]))
+    R = N + 4
+    rbits, nvar, vq, nops, order = (C.c_int * (3 * R))(), (C.c_int * R)(), (C.c_int * (3 * R))(), (C.c_int * R)(), (C.c_int * N)()
+    item_bits = (C.c_int * (9 * R))()
+    hl.hl_rounds.restype = C.c_int
+    nr = hl.hl_rounds(arr, N, (1 << K) - 1, 2, rbits, nvar, vq, nops, order, item_bits)
+    assert 0 < nr < N
+    flat = list(order[: sum(nops[:nr])])
+    live = [i for i in range(N) if ops[i].kind != OP_NOP]
+    assert sorted(flat) == live
+    pos = 0
+    for r in range(nr):
+        rb = set(rbits[3 * r: 3 * r + 3])
+        assert len(rb) == 3
+        var = set(vq[3 * r + j] for j in range(nvar[r]))
+        assert nvar[r] <= 2 and not (var & rb)
+        for i in flat[pos: pos + nops[r]]:
+            op = ops[i]
+            nd = set(op.tgt[j] for j in range(op.n_tgt)) if op.kind != OP_DIAG else set()
+            dg = set(op.ctrl[j] for j in range(op.n_ctrl)) | (set(op.tgt[j] for j in range(op.n_tgt)) if op.kind == OP_DIAG else set())
+            assert nd <= rb, "non-diagonal target outside the round's register bits"
+            assert dg <= (rb | var), "control / selector that is neither a register bit nor a variant bit"
+        pos += nops[r]
+        ib = list(item_bits[9 * r: 9 * r + K - 3])
+        assert sorted(ib) == sorted(set(range(K)) - rb)                      # bijection onto the other tile bits
+        assert len({b % 3 for b in ib[:3]}) == 3                             # quarter-warp hits 8 distinct bank groups
+        for v in var:                                                         # variant bits are warp-uniform item bits
+            assert ib.index(v) in (5, 6, 7)
+    psi = random_state(n, 9)
+    a = psi.copy()
+    for i in range(N):
+        a = apply_op(a, ops[i], n)
+    b = psi.copy()
+    for i in flat:
+        b = apply_op(b, ops[i], n)
+    assert np.max(np.abs(a - b)) < 1e-13
