@@ -151,27 +151,62 @@ inline std::vector<RoundPlan> schedule_rounds(const std::vector<Op>& all, const 
   std::vector<int> remaining = plan.ops;
   std::vector<RoundPlan> rounds;
   while (!remaining.empty()) {
-    uint64_t R = 0, V = 0;  // round qubits / variant qubits (masks over register qubits)
-    RoundPlan rp;
-    std::vector<int> left;
-    uint64_t blocked_nd = 0, blocked_d = 0;
-    for (int idx : remaining) {
-      const OpMasks m = masks_of(all[idx]);
-      const bool conflict = ((m.nd | m.dg) & blocked_nd) != 0 || (m.nd & blocked_d) != 0;
-      if (!conflict) {
-        const uint64_t nR = R | m.nd;
-        const uint64_t nV = (V | m.dg) & ~nR;
-        if (__builtin_popcountll(nR) <= 3 && __builtin_popcountll(nV) <= max_variant_bits) {
-          R = nR;
-          V = nV;
-          rp.ops.push_back(idx);
-          continue;
-        }
+    // Greedy fill from a seed: the seed's targets become register bits first, then ops are taken in
+    // program order.  Several seeds are tried (the first pending op, and the next few ops that
+    // commute with everything before them); the fill that absorbs the most ops wins.
+    struct Fill {
+      uint64_t R = 0, V = 0;
+      std::vector<int> ops, left;
+    };
+    auto fill_from = [&](int seed_pos) {
+      Fill f;
+      uint64_t blocked_nd = 0, blocked_d = 0;
+      if (seed_pos > 0) {  // reserve the seed's register bits before scanning
+        const OpMasks ms = masks_of(all[remaining[seed_pos]]);
+        f.R = ms.nd;
+        f.V = ms.dg & ~f.R;
       }
-      left.push_back(idx);
-      blocked_nd |= m.nd;
-      blocked_d |= m.dg;
+      for (size_t pos = 0; pos < remaining.size(); ++pos) {
+        const int idx = remaining[pos];
+        const OpMasks m = masks_of(all[idx]);
+        const bool conflict = ((m.nd | m.dg) & blocked_nd) != 0 || (m.nd & blocked_d) != 0;
+        if (!conflict) {
+          const uint64_t nR = f.R | m.nd;
+          const uint64_t nV = (f.V | m.dg) & ~nR;
+          if (__builtin_popcountll(nR) <= 3 && __builtin_popcountll(nV) <= max_variant_bits) {
+            f.R = nR;
+            f.V = nV;
+            f.ops.push_back(idx);
+            continue;
+          }
+        }
+        f.left.push_back(idx);
+        blocked_nd |= m.nd;
+        blocked_d |= m.dg;
+      }
+      return f;
+    };
+    Fill best = fill_from(0);
+    {
+      uint64_t blocked_nd = 0, blocked_d = 0;
+      int tried = 0;
+      for (size_t pos = 0; pos < remaining.size() && pos < 64 && tried < 6; ++pos) {
+        const OpMasks m = masks_of(all[remaining[pos]]);
+        const bool free_to_lead = ((m.nd | m.dg) & blocked_nd) == 0 && (m.nd & blocked_d) == 0;
+        if (pos > 0 && free_to_lead && m.nd != 0) {
+          ++tried;
+          Fill f = fill_from((int)pos);
+          // the seed must actually have been absorbed, and the first pending op must not starve
+          if (f.ops.size() > best.ops.size()) best = f;
+        }
+        blocked_nd |= m.nd;
+        blocked_d |= m.dg;
+      }
     }
+    uint64_t R = best.R, V = best.V;
+    RoundPlan rp;
+    rp.ops = best.ops;
+    std::vector<int> left = best.left;
     // free register slots: promote variant qubits that live in the tile (halves the matrix count
     // for free), then pad with unused tile bits
     for (int q = 0; q < 64 && __builtin_popcountll(R) < 3; ++q)

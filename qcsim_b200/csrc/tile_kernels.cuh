@@ -28,7 +28,7 @@
 namespace qcsim {
 
 constexpr int kRoundBits = 3;      // amplitudes per thread per round = 2^3
-constexpr int kMaxVariantBits = 2; // matrices per round <= 2^2
+constexpr int kMaxVariantBits = 3; // matrices per round <= 2^3
 constexpr int kMaxTileRounds = 7;  // per launch: 7 rounds x 4 matrices x 1 KiB fits the 32 KiB parameter block
 constexpr int kMaxTileMats = 28;
 constexpr int kRoundMatAmps = 64;  // one 8x8 complex matrix
