@@ -382,8 +382,15 @@ int engine_apply_now(qcsim_sv* h, const Op& op) {
 
 int engine_enqueue(qcsim_sv* h, const Op& op) {
   if (op.kind != OP_NOP) h->queue.push_back(op);
-  if (h->queue.size() >= 4096) return engine_flush(h);
-  return QCSIM_OK;
+  if (h->queue.size() < 16384) return QCSIM_OK;
+  // The queue is bounded.  A QFT gate stream that is still arriving is recognised as a whole
+  // (planner.h: match_qft), so its prefix stays queued instead of being cut here.
+  std::vector<Op> head;
+  head.swap(h->queue);
+  std::vector<Op> tail;
+  const int rc = fusion_execute_partial(h, head, head.size() < 65536 ? &tail : nullptr);
+  h->queue.insert(h->queue.begin(), tail.begin(), tail.end());
+  return rc;
 }
 
 void engine_drop_queue(qcsim_sv* h) { h->queue.clear(); }

@@ -184,7 +184,11 @@ static int execute_plain(qcsim_sv* h, const std::vector<Op>& ops) {
   return fusion_execute_local(h, ops);
 }
 
-int fusion_execute(qcsim_sv* h, const std::vector<Op>& ops_in) {
+int fusion_execute(qcsim_sv* h, const std::vector<Op>& ops_in) { return fusion_execute_partial(h, ops_in, nullptr); }
+
+// `deferred` != nullptr: a trailing run of ops that is still a valid QFT prefix when the list ends is
+// handed back instead of executed (the caller keeps it queued until the rest of the transform arrives).
+int fusion_execute_partial(qcsim_sv* h, const std::vector<Op>& ops_in, std::vector<Op>* deferred) {
   // QFT / IQFT gate streams (QCSim's own QuantumFourierTransform emits them gate by gate) run as
   // radix-8 FFT passes; everything around them goes through the gate-block planner
   static const int no_qft = env_int("QCSIM_QFT_GENERIC", 0);
@@ -195,12 +199,17 @@ int fusion_execute(qcsim_sv* h, const std::vector<Op>& ops_in) {
     const Op& op = ops_in[i];
     const bool candidate = op.n_ctrl == 0 && op.kind == OP_PAIR;  // a pattern starts with H or SWAP
     QftMatch m;
-    if (candidate) m = match_qft(ops_in, i);
-    if (m.length > 0) {
+    bool ran_off = false;
+    if (candidate) m = match_qft(ops_in, i, 4, &ran_off);
+    const bool touches_end = i + m.length == ops_in.size();  // more of the transform (or its swaps) may still arrive
+    if (m.length > 0 && !(deferred && touches_end)) {
       QCSIM_TRY(execute_plain(h, plain));
       plain.clear();
       QCSIM_TRY(engine_qft_direct(h, m.sq, m.eq, m.do_swap, m.inverse));
       i += m.length;
+    } else if (deferred && (ran_off || m.length > 0)) {
+      deferred->assign(ops_in.begin() + i, ops_in.end());
+      break;
     } else {
       plain.push_back(op);
       ++i;

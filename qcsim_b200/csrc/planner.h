@@ -299,9 +299,15 @@ inline int match_swaps(const std::vector<Op>& ops, size_t i, int sq, int eq) {
 }  // namespace detail
 
 // Tries to match a QFT / IQFT of at least `min_qubits` qubits starting exactly at ops[i].
-inline QftMatch match_qft(const std::vector<Op>& ops, size_t i, int min_qubits = 4) {
+// *ran_off_end (optional) is set when the stream was still a valid QFT prefix at the end of `ops`.
+inline QftMatch match_qft(const std::vector<Op>& ops, size_t i, int min_qubits = 4, bool* ran_off_end = nullptr) {
   using namespace detail;
   QftMatch none;
+  if (ran_off_end) *ran_off_end = false;
+  auto off = [&](size_t p) {  // true when position p is past the end (and remembers it)
+    if (p >= ops.size() && ran_off_end) *ran_off_end = true;
+    return p >= ops.size();
+  };
   const double pi_2 = 1.57079632679489661923;  // M_PI_2
   const size_t N = ops.size();
   int q0 = 0;
@@ -312,7 +318,7 @@ inline QftMatch match_qft(const std::vector<Op>& ops, size_t i, int min_qubits =
     size_t j = i + 1;
     double phase = pi_2;
     int ctrl = eq - 1;
-    while (j < N && ctrl >= 0 && is_cphase_op(ops[j], eq, ctrl, phase)) {
+    while (!off(j) && ctrl >= 0 && is_cphase_op(ops[j], eq, ctrl, phase)) {
       ++j;
       --ctrl;
       phase *= 0.5;
@@ -324,12 +330,12 @@ inline QftMatch match_qft(const std::vector<Op>& ops, size_t i, int min_qubits =
       for (int cur = eq; cur > sq && ok; --cur) {
         double ph = pi_2;
         for (int c = cur - 1; c >= sq && ok; --c) {
-          ok = p < N && is_cphase_op(ops[p], cur, c, ph);
+          ok = !off(p) && is_cphase_op(ops[p], cur, c, ph);
           ++p;
           ph *= 0.5;
         }
         int hq = -1;
-        ok = ok && p < N && is_hadamard_op(ops[p], &hq) && hq == cur - 1;
+        ok = ok && !off(p) && is_hadamard_op(ops[p], &hq) && hq == cur - 1;
         ++p;
       }
       if (ok) {
@@ -368,12 +374,12 @@ inline QftMatch match_qft(const std::vector<Op>& ops, size_t i, int min_qubits =
       double ph = -pi_2;
       bool ok = true;
       for (int c = cur - 1; c >= sq && ok; --c) {
-        ok = pp < N && is_cphase_op(ops[pp], cur, c, ph);
+        ok = !off(pp) && is_cphase_op(ops[pp], cur, c, ph);
         ++pp;
         ph *= 0.5;
       }
       int hq = -1;
-      ok = ok && pp < N && is_hadamard_op(ops[pp], &hq) && hq == cur;
+      ok = ok && !off(pp) && is_hadamard_op(ops[pp], &hq) && hq == cur;
       if (!ok) break;
       p = pp + 1;
       ++cur;
