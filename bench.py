@@ -336,6 +336,28 @@ def kernel_sweep(reg, lib, h, stream, n_local, torch):
         ms = e0.elapsed_time(e1) / reps
         gbs = bytes_per_amp * (1 << n_local) / (ms * 1e-3) / 1e9
         out[name] = {"ms": round(ms, 4), "algo_bytes_per_amp": bytes_per_amp, "GBps": round(gbs, 1), "frac_of_peak": round(gbs / peak, 4)}
+    # measurement path (read-only reductions: 16 B per amplitude)
+    import ctypes as C2
+    outd, outu = C2.c_double(), C2.c_uint64()
+    reductions = {
+        "GetQubitProbability q=mid": lambda: lib.qcsim_sv_qubit_probability(h, n_local // 2, C2.byref(outd)),
+        "MeasureAll scan (no collapse)": lambda: lib.qcsim_sv_measure_all_nocollapse(h, 0.4375, C2.byref(outu)),
+    }
+    for name, fn in reductions.items():
+        for _ in range(2):
+            _lib.check(fn())
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        e0.record(stream)
+        for _ in range(reps):
+            _lib.check(fn())
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        bpa = 8 if name.startswith("GetQubitProbability") else 16  # only the amplitudes with the qubit set are read
+        gbs = bpa * (1 << n_local) / (ms * 1e-3) / 1e9
+        out[name] = {"ms": round(ms, 4), "algo_bytes_per_amp": bpa, "GBps": round(gbs, 1), "frac_of_peak": round(gbs / peak, 4),
+                     "note": "includes the host round trip of the result"}
     return out
 
 

@@ -733,9 +733,44 @@ int engine_pick_state(qcsim_sv* h, double prob, uint64_t fallback, uint64_t* out
 }
 
 int engine_sample(qcsim_sv* h, const double* probs, uint64_t count, uint64_t* outcomes) {
-  // one scan per draw for now; the chunk masses are recomputed each time (state is unchanged)
-  for (uint64_t i = 0; i < count; ++i) QCSIM_TRY(engine_pick_state(h, probs[i], 0, &outcomes[i]));
-  return QCSIM_OK;
+  // RepeatedMeasure (QubitRegister.h:227-273): many draws against ONE cumulative table.  The chunk
+  // masses (the only pass over the state) are computed once; every draw then costs two single-block
+  // kernels (scan of the chunk masses, scan inside the selected chunk) and 8 bytes back to the host.
+  if (count == 0) return QCSIM_OK;
+  QCSIM_TRY(engine_canonicalize(h));
+  if (h->world > 1 || h->strict_measure) {
+    for (uint64_t i = 0; i < count; ++i) QCSIM_TRY(engine_pick_state(h, probs[i], 0, &outcomes[i]));
+    return QCSIM_OK;
+  }
+  const int g = (int)std::min<uint64_t>(h->n_chunks, (uint64_t)kMaxPartials);
+  k_chunk_sums<<<g, kThreads, 0, h->stream>>>(h->psi, h->dim_local, h->n_chunks, h->d_chunk_sums);
+  CUDA_TRY(cudaGetLastError());
+  h->stats.kernel_launches += 1;
+  h->stats.state_passes += 1;
+  h->stats.bytes_moved += 16ULL * h->dim_local;
+  const uint64_t batch = 4096 / sizeof(ScanResult);  // results staged through the 4 KiB pinned buffer
+  ScanResult* d_res = nullptr;
+  CUDA_TRY(cudaMalloc(&d_res, batch * sizeof(ScanResult)));
+  ScanResult* stage = (ScanResult*)h->h_pinned;
+  int rc = QCSIM_OK;
+  for (uint64_t i0 = 0; i0 < count && rc == QCSIM_OK; i0 += batch) {
+    const uint64_t nb = std::min<uint64_t>(batch, count - i0);
+    for (uint64_t j = 0; j < nb; ++j) {
+      k_find_chunk<<<1, 1024, 0, h->stream>>>(h->d_chunk_sums, h->n_chunks, dd_make(0, 0), probs[i0 + j], d_res + j);
+      k_find_in_chunk<<<1, kThreads, 0, h->stream>>>(h->psi, h->dim_local, probs[i0 + j], d_res + j);
+    }
+    h->stats.kernel_launches += 2 * nb;
+    cudaError_t ce = cudaGetLastError();
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(stage, d_res, nb * sizeof(ScanResult), cudaMemcpyDeviceToHost, h->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(h->stream);
+    if (ce != cudaSuccess) {
+      rc = fail(QCSIM_ERR_CUDA, "sample: %s", cudaGetErrorString(ce));
+      break;
+    }
+    for (uint64_t j = 0; j < nb; ++j) outcomes[i0 + j] = stage[j].found ? stage[j].index : 0;  // fallback 0, QubitRegister.h:623
+  }
+  cudaFree(d_res);
+  return rc;
 }
 
 }  // namespace qcsim

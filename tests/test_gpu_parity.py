@@ -357,3 +357,34 @@ def test_fusion_mode_flushes_on_observation():
                 p = draws(1, i)[0]
                 assert gpu.measure(0, 2, p) == ref.measure(0, 2, p)
         assert maxdiff(gpu.state(), ref.state()) <= TOL
+
+
+@pytest.mark.parametrize("n", [5, 13, 18])
+def test_repeated_measure_equals_the_reference_draw_by_draw(n):
+    """RepeatedMeasure (QubitRegister.h:227-273) = many draws against one cumulative table: every
+    shot must be the outcome the reference's MeasureNoCollapse gives for the same draw."""
+    psi0 = random_state(n, 23)
+    shots = 300
+    with oracle.best_oracle(n) as ref, GpuSim(n) as gpu:
+        ref.set_state(psi0)
+        gpu.set_state(psi0)
+        gpu.reg.rng.seed(1234)
+        hist = gpu.reg.RepeatedMeasure(shots)
+        gpu.reg.rng.seed(1234)
+        d = [gpu.reg._draw() for _ in range(shots)]  # the draws RepeatedMeasure consumed
+        want = {}
+        for p in d:
+            s = ref.measure_all_nocollapse(p)
+            want[s] = want.get(s, 0) + 1
+        assert hist == dict(sorted(want.items()))
+        assert sum(hist.values()) == shots
+        # sub-register variant: outcomes masked and shifted (QubitRegister.h:325-375)
+        gpu.reg.rng.seed(99)
+        sub = gpu.reg.RepeatedMeasure(1, n - 2, 50)
+        gpu.reg.rng.seed(99)
+        want = {}
+        for _ in range(50):
+            s = (ref.measure_all_nocollapse(gpu.reg._draw()) >> 1) & ((1 << (n - 2)) - 1)
+            want[s] = want.get(s, 0) + 1
+        assert sub == dict(sorted(want.items()))
+        assert maxdiff(gpu.state(), psi0) == 0.0  # sampling does not touch the state
