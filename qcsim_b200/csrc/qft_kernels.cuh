@@ -397,4 +397,78 @@ static __global__ void __launch_bounds__(kTileThreads, 3) k_tile_permute(amp* __
   }
 }
 
+// ---- full qubit reversal in ONE pass (COBRA-style) -----------------------------------------------------
+// QubitsSwapper::Swap on qubits [0, m) (QubitsSwapper.h:23-34) maps index bits (a : u : c) -- top 6,
+// middle m-12, low 6 -- to (rev c : rev u : rev a).  A CTA takes the two 4096-amplitude tiles with
+// middle values u and rev(u) (64 runs of 1 KiB each), keeps both in shared memory, and writes each
+// to the other's place with the (a, c) roles exchanged and bit-reversed: every amplitude is read
+// once and written once, all global accesses are 1 KiB runs.  Shared-memory slot of element (a, c):
+// row rev6(c), column a ^ (a >> 3) ^ (row >> 2 & 7), which keeps both the transposing stores and
+// the row-wise loads free of bank conflicts.
+struct BitRevArgs {
+  int m;            // qubits [0, m) are reversed, m >= 12
+  int n_local;
+  uint64_t n_work;  // 2^(n_local - 12): (outer bits above m) x (middle value)
+};
+
+__device__ __forceinline__ uint32_t rev6(uint32_t x) { return __brev(x) >> 26; }
+__device__ __forceinline__ uint32_t cobra_slot(uint32_t a, uint32_t c) {
+  const uint32_t row = rev6(c);
+  return row * 64u + ((a ^ (a >> 3) ^ ((row >> 2) & 7u)) & 63u);
+}
+
+static __global__ void __launch_bounds__(kTileThreads, 1) k_bit_reverse(amp* __restrict__ psi, const __grid_constant__ BitRevArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  amp* bufA = reinterpret_cast<amp*>(smem_raw);
+  amp* bufB = bufA + 4096;
+  const int mid_bits = A.m - 12;
+  const uint32_t tid = threadIdx.x;
+  const uint32_t c2 = (tid & 31u) * 2u, a_lo = tid >> 5;  // this thread's column pair and row within an 8-row slab
+  for (uint64_t w = blockIdx.x; w < A.n_work; w += gridDim.x) {
+    const uint64_t u = w & ((1ULL << mid_bits) - 1ULL);
+    const uint64_t o = w >> mid_bits;
+    const uint64_t ur = mid_bits ? (__brevll(u) >> (64 - mid_bits)) : 0ULL;
+    if (u > ur) continue;  // the pair is handled by the CTA that drew the smaller middle value
+    const uint64_t base_u = (o << A.m) | (u << 6), base_r = (o << A.m) | (ur << 6);
+    const int hi = A.m - 6;  // position of the `a` field
+    amp2 x[8], y[8];
+#pragma unroll
+    for (uint32_t it = 0; it < 8; ++it) x[it] = ld_amp2(psi + (base_u | ((uint64_t)(it * 8u + a_lo) << hi) | c2));
+    if (u != ur) {
+#pragma unroll
+      for (uint32_t it = 0; it < 8; ++it) y[it] = ld_amp2(psi + (base_r | ((uint64_t)(it * 8u + a_lo) << hi) | c2));
+    }
+#pragma unroll
+    for (uint32_t it = 0; it < 8; ++it) {
+      const uint32_t a = it * 8u + a_lo;
+      bufA[cobra_slot(a, c2)] = x[it].a;
+      bufA[cobra_slot(a, c2 + 1u)] = x[it].b;
+      if (u != ur) {
+        bufB[cobra_slot(a, c2)] = y[it].a;
+        bufB[cobra_slot(a, c2 + 1u)] = y[it].b;
+      }
+    }
+    __syncthreads();
+    // output element (a', c') of the tile at rev(u) is input element (rev6 c', rev6 a') of the tile at u:
+    // slot row = rev6(rev6 a') = a', column from a = rev6(c')
+#pragma unroll
+    for (uint32_t it = 0; it < 8; ++it) {
+      const uint32_t ap = it * 8u + a_lo;
+      const uint32_t sw = (ap >> 2) & 7u;
+      const uint32_t col0 = rev6(c2), col1 = col0 | 32u;
+      const uint32_t s0 = ap * 64u + ((col0 ^ (col0 >> 3) ^ sw) & 63u), s1 = ap * 64u + ((col1 ^ (col1 >> 3) ^ sw) & 63u);
+      amp2 v;
+      v.a = bufA[s0];
+      v.b = bufA[s1];
+      st_amp2(psi + (base_r | ((uint64_t)ap << hi) | c2), v);
+      if (u != ur) {
+        v.a = bufB[s0];
+        v.b = bufB[s1];
+        st_amp2(psi + (base_u | ((uint64_t)ap << hi) | c2), v);
+      }
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace qcsim
