@@ -93,7 +93,6 @@ int engine_destroy(qcsim_sv* h) {
   if (!h) return QCSIM_OK;
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->world > 1) dist_shutdown(h);
-  fusion_release(h);
   cudaFree(h->psi);
   cudaFree(h->saved);
   cudaFree(h->d_partials);

@@ -61,12 +61,6 @@ struct qcsim_sv {
   bool strict_measure = false;
   std::vector<qcsim::Op> queue;  // deferred gates (fusion mode / apply_batch)
 
-  // pinned + device staging for fused-pass descriptors (fusion.cu)
-  void* fuse_stage_host = nullptr;
-  void* fuse_stage_dev = nullptr;
-  size_t fuse_stage_bytes = 0;
-  void* fuse_stage_event = nullptr;
-
   void* nccl_comm = nullptr;     // ncclComm_t when world > 1
   void* dist = nullptr;          // sharding state (dist.cu)
 

@@ -1,12 +1,13 @@
-// fusion.cu -- gate-stream planner and launcher for fused gate blocks (see fusion.h, tile_kernels.cuh).
+// fusion.cu -- gate-stream execution: QFT recognition, pass planning, round matrices, launches
+// (see fusion.h, planner.h, tile_kernels.cuh).
 //
-// Planning is greedy and order-preserving:
-//   * walk the pending ops in program order and grow a tile-qubit set T (low L qubits fixed);
-//     an op is absorbed into the current pass when its non-diagonal targets fit into T and it
-//     commutes with every op that was skipped before it (two ops commute when, on every qubit
-//     they share, both act diagonally -- as a control or a diagonal selector);
-//   * absorbed ops keep their relative order and are cut into rounds of <= 3 target bits;
-//   * a pass that would not save HBM traffic over running its ops one by one is not fused.
+//   * fusion_execute      : cuts QFT / IQFT gate streams out of the list (planner.h: match_qft) and
+//                           runs them as radix-8 passes; the rest goes to the sharded planner or to
+//   * fusion_execute_local: plan_passes (greedy, order-preserving: an op joins the current pass when
+//                           its non-diagonal targets fit the tile and it commutes with every op
+//                           skipped before it), then per pass schedule_rounds + one 8x8 matrix per
+//                           round and variant (apply_small), then k_tile_pass;
+//   * a pass whose rounds would cost more than its gates run one by one is executed unfused.
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -91,9 +92,6 @@ static void apply_small(const Op& op, const int* rpos, const int* vval, cplx* ve
     default: break;
   }
 }
-
-int fusion_reserve(qcsim_sv*) { return QCSIM_OK; }
-void fusion_release(qcsim_sv*) {}
 
 // Build the round matrices + parameter block of one pass and launch it.  A launch holds at most
 // kMaxTileRounds rounds / kMaxTileMats matrices (parameter-block limit); a longer pass is cut into

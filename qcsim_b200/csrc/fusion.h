@@ -15,8 +15,6 @@ int fusion_execute_partial(qcsim_sv* h, const std::vector<Op>& ops, std::vector<
 
 // same, for ops whose qubit indices are already physical bit positions of the local slice
 int fusion_execute_local(qcsim_sv* h, const std::vector<Op>& ops);
-int fusion_reserve(qcsim_sv* h);
-void fusion_release(qcsim_sv* h);
 int dist_execute(qcsim_sv* h, const std::vector<Op>& ops);
 
 int engine_launch_local(qcsim_sv* h, const Op& op);
