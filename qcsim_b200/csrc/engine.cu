@@ -99,6 +99,7 @@ int engine_destroy(qcsim_sv* h) {
   cudaFree(h->d_scalars);
   cudaFree(h->d_chunk_sums);
   cudaFree(h->d_scan);
+  cudaFree(h->d_qft_table);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -488,7 +489,7 @@ int engine_qft_passes(qcsim_sv* h, int sq, int eq, bool inverse, uint64_t rank_b
   }
   static bool attr_set = false;
   if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(k_qft_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(k_qft_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 65 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(k_tile_permute, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     attr_set = true;
   }
@@ -524,9 +525,11 @@ int engine_qft_passes(qcsim_sv* h, int sq, int eq, bool inverse, uint64_t rank_b
       const uint32_t reg_mask = ((1u << G.size) - 1u) << lbit;
       item_bit_order(k, reg_mask, G.tb, 3);
     }
-    const size_t smem = (sizeof(amp) << k) + sizeof(amp) * ((k == 12 ? kMaxQftGroups * kQftItems3 : 0) + kMaxQftGroups);
-    const uint64_t grid = std::min<uint64_t>(A.n_tiles, (uint64_t)kNumSMs * 2);
-    k_qft_pass<<<(unsigned)grid, kTileThreads, smem, h->stream>>>(h->psi, A);
+    const size_t smem = (sizeof(amp) << k) + sizeof(amp) * kMaxQftGroups;
+    const uint64_t grid = std::min<uint64_t>(A.n_tiles, (uint64_t)kNumSMs * 3);
+    if (!h->d_qft_table) CUDA_TRY(cudaMalloc(&h->d_qft_table, sizeof(amp) * kMaxQftGroups * kQftItems3));
+    if (k == 12) k_qft_item_table<<<kMaxQftGroups * kQftItems3 / 256, 256, 0, h->stream>>>(h->d_qft_table, A);
+    k_qft_pass<<<(unsigned)grid, kTileThreads, smem, h->stream>>>(h->psi, h->d_qft_table, A);
     CUDA_TRY(cudaGetLastError());
     count_pass(h, h->dim_local);
     h->stats.fused_rounds += p.groups.size();

@@ -56,6 +56,7 @@ struct qcsim_sv {
   uint64_t n_chunks = 0;
   qcsim::ScanResult* d_scan = nullptr;
   void* h_pinned = nullptr;      // 4 KiB pinned staging for scalar results
+  qcsim::amp* d_qft_table = nullptr;  // per-pass item twiddle table of the QFT kernel (32 KiB)
 
   bool fusion = false;
   bool strict_measure = false;

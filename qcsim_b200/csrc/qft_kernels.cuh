@@ -65,27 +65,16 @@ __device__ __forceinline__ void hadamard_pair(amp& a, amp& b, double s) {
 template <int G>
 __device__ __forceinline__ void qft_group(amp (&v)[8], const QftPassArgs& A, bool inverse, amp P) {
   constexpr int N = 1 << G;
-  // powers of the twiddle base: amp x gets P^rev(x)
-  amp pw[8];
-  pw[1] = P;
-  if (G >= 2) {
-    pw[2] = cmul(P, P);
-    pw[3] = cmul(pw[2], P);
-  }
-  if (G >= 3) {
-    pw[4] = cmul(pw[2], pw[2]);
-    pw[5] = cmul(pw[4], P);
-    pw[6] = cmul(pw[3], pw[3]);
-    pw[7] = cmul(pw[6], P);
-  }
+  // amp x gets P^rev(x) = prod over set bits b of x of P^(2^(G-1-b)): the top register bit takes P,
+  // the next one P^2, the lowest P^4 -- one power of P live at a time (register pressure)
   auto twiddle = [&]() {
+    amp pw = P;
 #pragma unroll
-    for (int x = 1; x < N; ++x) {
-      int rev = 0;
+    for (int b = G - 1; b >= 0; --b) {
 #pragma unroll
-      for (int b = 0; b < G; ++b)
-        if ((x >> b) & 1) rev |= 1 << (G - 1 - b);
-      v[x] = cmul(v[x], pw[rev]);
+      for (int x = 0; x < N; ++x)
+        if ((x >> b) & 1) v[x] = cmul(v[x], pw);
+      if (b > 0) pw = cmul(pw, pw);
     }
   };
   auto hadamard = [&](int bit) {
@@ -133,8 +122,10 @@ __device__ __forceinline__ void qft_group(amp (&v)[8], const QftPassArgs& A, boo
   }
 }
 
-// Shared memory: tile (2^k amps) | per-item thread-part twiddles of the 3-qubit groups
-// (kMaxQftGroups x 512 amps, only when k == 12) | per-tile CTA-part twiddles (kMaxQftGroups amps).
+// Shared memory: tile (2^k amps) | per-tile CTA-part twiddles (kMaxQftGroups amps).  The thread part
+// of the twiddles of 3-qubit groups in 12-bit tiles depends on the item only: it is tabulated once
+// per pass in global memory (k_qft_item_table, 32 KiB, L1-resident) so that the tile kernel fits
+// three CTAs per SM.
 constexpr int kQftItems3 = 512;  // items of a 3-qubit group in a 12-bit tile
 
 __device__ __forceinline__ uint64_t qft_logical(const QftPassArgs& A, uint64_t phys) {
@@ -162,13 +153,32 @@ __device__ __forceinline__ amp qft_base(const QftPassArgs& A, const QftGroup& gr
   return make_amp(cs, inverse ? -sn : sn);
 }
 
-static __global__ void __launch_bounds__(kTileThreads, 2) k_qft_pass(amp* __restrict__ psi, const __grid_constant__ QftPassArgs A) {
+__device__ __forceinline__ uint64_t qft_phys_of_local(const QftPassArgs& A, uint32_t lbase) {
+  const uint32_t low_mask = (1u << A.low_identity) - 1u;
+  uint64_t phys = lbase & low_mask;
+#pragma unroll 1
+  for (int j = A.low_identity; j < A.k; ++j) phys |= (uint64_t)((lbase >> j) & 1u) << A.tpos[j];
+  return phys;
+}
+
+// table[g * 512 + item] = thread part of the twiddle base of item `item` of group g (12-bit tiles)
+static __global__ void k_qft_item_table(amp* __restrict__ table, const __grid_constant__ QftPassArgs A) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int gi = i / kQftItems3;
+  if (gi >= A.n_groups) return;
+  const QftGroup grp = A.groups[gi];
+  if (grp.size != 3) return;
+  const uint32_t lbase = qft_lbase(grp, i % kQftItems3);
+  table[i] = qft_base(A, grp, qft_logical(A, qft_phys_of_local(A, lbase)), A.inverse != 0);
+}
+
+static __global__ void __launch_bounds__(kTileThreads, 3) k_qft_pass(amp* __restrict__ psi, const amp* __restrict__ tw_item,
+                                                                      const __grid_constant__ QftPassArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   amp* tile = reinterpret_cast<amp*>(smem_raw);
   const int k = A.k;
   const uint32_t tile_amps = 1u << k;
-  amp* tw_item = tile + tile_amps;                              // [group][item], k == 12 only
-  amp* tw_cta = tw_item + (k == 12 ? kMaxQftGroups * kQftItems3 : 0);  // [group]
+  amp* tw_cta = tile + tile_amps;  // [group]
   const int L = A.low_identity;
   const uint32_t low_mask = (1u << L) - 1u;
   const uint32_t tid = threadIdx.x;
@@ -183,31 +193,6 @@ static __global__ void __launch_bounds__(kTileThreads, 2) k_qft_pass(amp* __rest
   const uint32_t n_it = (tile_amps >> 1) > kTileThreads ? (tile_amps >> 1) / kTileThreads : 1u;
   const bool mover = (tid << 1) < tile_amps;
 
-  // thread-part twiddles: depend on the item's tile bits only, so once per kernel
-  if (tabled) {
-#pragma unroll 1
-    for (int gi = 0; gi < A.n_groups; ++gi) {
-      const QftGroup grp = A.groups[gi];
-      if (grp.size != 3) continue;
-#pragma unroll 1
-      for (uint32_t item = tid; item < kQftItems3; item += kTileThreads) {
-        const uint32_t lbase = qft_lbase(grp, item);
-        uint64_t phys = lbase & low_mask;
-#pragma unroll 1
-        for (int j = L; j < k; ++j) phys |= (uint64_t)((lbase >> j) & 1u) << A.tpos[j];
-        tw_item[gi * kQftItems3 + item] = qft_base(A, grp, qft_logical(A, phys), inverse);
-      }
-    }
-  }
-
-  // swizzled tile offsets (in bytes) of this thread's two items per 3-qubit group: once per kernel
-  uint32_t slb[kMaxQftGroups][2];
-#pragma unroll
-  for (int gi = 0; gi < kMaxQftGroups; ++gi)
-#pragma unroll
-    for (int it = 0; it < 2; ++it) slb[gi][it] = (tabled && gi < A.n_groups) ? (swz(qft_lbase(A.groups[gi], tid + it * kTileThreads)) << 4) : 0u;
-  unsigned char* const tile_bytes = smem_raw;
-
   for (uint64_t t = blockIdx.x; t < A.n_tiles; t += gridDim.x) {
     uint64_t gbase = t;
 #pragma unroll 1
@@ -217,10 +202,10 @@ static __global__ void __launch_bounds__(kTileThreads, 2) k_qft_pass(amp* __rest
 
     if (mover) {
 #pragma unroll 1
-      for (uint32_t it0 = 0; it0 < n_it; it0 += 8) {  // 8 loads in flight per thread
-        amp2 x[8];
+      for (uint32_t it0 = 0; it0 < n_it; it0 += 4) {  // 4 loads in flight per thread (x 3 CTAs per SM)
+        amp2 x[4];
 #pragma unroll
-        for (uint32_t u = 0; u < 8; ++u) {
+        for (uint32_t u = 0; u < 4; ++u) {
           const uint32_t lv = (it0 + u) << 9;
           uint64_t gv = 0;
 #pragma unroll 1
@@ -228,7 +213,7 @@ static __global__ void __launch_bounds__(kTileThreads, 2) k_qft_pass(amp* __rest
           if (it0 + u < n_it) x[u] = ld_amp2(psi + (gbase | g_fixed | gv));
         }
 #pragma unroll
-        for (uint32_t u = 0; u < 8; ++u) {
+        for (uint32_t u = 0; u < 4; ++u) {
           if (it0 + u >= n_it) continue;
           const uint32_t s = s_fixed ^ swz((it0 + u) << 9);
           tile[s] = x[u].a;
@@ -238,40 +223,22 @@ static __global__ void __launch_bounds__(kTileThreads, 2) k_qft_pass(amp* __rest
     }
     __syncthreads();
 
-#pragma unroll
-    for (int gi = 0; gi < kMaxQftGroups; ++gi) {
-      if (gi >= A.n_groups) break;
+#pragma unroll 1
+    for (int gi = 0; gi < A.n_groups; ++gi) {
       const QftGroup grp = A.groups[gi];
       const int G = grp.size;
       const uint32_t items = tile_amps >> G;
       const uint32_t so0 = swz(1u << grp.lbit), so1 = swz(2u << grp.lbit), so2 = swz(4u << grp.lbit);
       const amp p_cta = tw_cta[gi];
-      if (tabled && G == 3) {
-        // fast path (12-bit tile, 3-qubit group): two items per thread, addresses and the thread part
-        // of the twiddle precomputed; per amplitude one XOR + LDS + STS around the butterfly
-        uint32_t cb[8];
-#pragma unroll
-        for (int x = 0; x < 8; ++x) cb[x] = (((x & 1) ? so0 : 0u) ^ ((x & 2) ? so1 : 0u) ^ ((x & 4) ? so2 : 0u)) << 4;
-#pragma unroll
-        for (int it = 0; it < 2; ++it) {
-          const amp P = cmul(p_cta, tw_item[gi * kQftItems3 + tid + it * kTileThreads]);
-          amp v[8];
-#pragma unroll
-          for (int x = 0; x < 8; ++x) v[x] = *reinterpret_cast<const amp*>(tile_bytes + (slb[gi][it] ^ cb[x]));
-          qft_group<3>(v, A, inverse, P);
-#pragma unroll
-          for (int x = 0; x < 8; ++x) *reinterpret_cast<amp*>(tile_bytes + (slb[gi][it] ^ cb[x])) = v[x];
-        }
-        __syncthreads();
-        continue;
-      }
 #pragma unroll 1
       for (uint32_t item = tid; item < items; item += kTileThreads) {
         const uint32_t lbase = qft_lbase(grp, item);
-        uint64_t phys = gbase | A.rank_bits | (lbase & low_mask);
-#pragma unroll 1
-        for (int j = L; j < k; ++j) phys |= (uint64_t)((lbase >> j) & 1u) << A.tpos[j];
-        const amp P = qft_base(A, grp, qft_logical(A, phys), inverse);
+        amp P;
+        if (tabled && G == 3) {
+          P = cmul(p_cta, __ldg(tw_item + gi * kQftItems3 + item));
+        } else {
+          P = qft_base(A, grp, qft_logical(A, gbase | A.rank_bits | qft_phys_of_local(A, lbase)), inverse);
+        }
         const uint32_t sl = swz(lbase);
         amp v[8];
         if (G == 3) {
