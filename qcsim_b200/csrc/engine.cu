@@ -666,18 +666,14 @@ static int engine_qft_generic(qcsim_sv* h, int sq, int eq, bool do_swap, bool in
 int engine_reverse_bits(qcsim_sv* h, int sq, int eq) {
   const int m = eq - sq + 1;
   static const bool no_cobra = std::getenv("QCSIM_NO_COBRA") != nullptr;
-  if (sq == 0 && m >= 12 && !no_cobra) {  // whole-register style reversal: one pass (k_bit_reverse)
-    static bool attr_set = false;
-    if (!attr_set) {
-      CUDA_TRY(cudaFuncSetAttribute(k_bit_reverse, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
-      attr_set = true;
-    }
+  if (sq == 0 && m >= 2 * kRevT && !no_cobra) {  // whole-register style reversal: one pass (k_bit_reverse)
+    const size_t smem = 2 * sizeof(amp) << (2 * kRevT);
     BitRevArgs A;
     A.m = m;
     A.n_local = h->n_local;
-    A.n_work = 1ULL << (h->n_local - 12);
-    const uint64_t grid = std::min<uint64_t>(A.n_work, (uint64_t)kNumSMs);
-    k_bit_reverse<<<(unsigned)grid, kTileThreads, 128 * 1024, h->stream>>>(h->psi, A);
+    A.n_work = 1ULL << (h->n_local - 2 * kRevT);
+    const uint64_t grid = std::min<uint64_t>(A.n_work, (uint64_t)kNumSMs * 4);
+    k_bit_reverse<<<(unsigned)grid, kTileThreads, smem, h->stream>>>(h->psi, A);
     CUDA_TRY(cudaGetLastError());
     count_pass(h, h->dim_local);
     return QCSIM_OK;

@@ -365,65 +365,74 @@ static __global__ void __launch_bounds__(kTileThreads, 3) k_tile_permute(amp* __
 }
 
 // ---- full qubit reversal in ONE pass (COBRA-style) -----------------------------------------------------
-// QubitsSwapper::Swap on qubits [0, m) (QubitsSwapper.h:23-34) maps index bits (a : u : c) -- top 6,
-// middle m-12, low 6 -- to (rev c : rev u : rev a).  A CTA takes the two 4096-amplitude tiles with
-// middle values u and rev(u) (64 runs of 1 KiB each), keeps both in shared memory, and writes each
+// QubitsSwapper::Swap on qubits [0, m) (QubitsSwapper.h:23-34) maps index bits (a : u : c) -- top T,
+// middle m-2T, low T -- to (rev c : rev u : rev a).  A CTA takes the two 2^T x 2^T tiles with middle
+// values u and rev(u) (2^T runs of 2^T amplitudes each), keeps both in shared memory, and writes each
 // to the other's place with the (a, c) roles exchanged and bit-reversed: every amplitude is read
-// once and written once, all global accesses are 1 KiB runs.  Shared-memory slot of element (a, c):
-// row rev6(c), column a ^ (a >> 3) ^ (row >> 2 & 7), which keeps both the transposing stores and
-// the row-wise loads free of bank conflicts.
+// once and written once, all global accesses are 2^T x 16 B runs (T = 5: 512 B).  Shared-memory slot
+// of element (a, c): row revT(c), column a ^ (a >> 3) ^ (row >> (T-4) & 7), which keeps both the
+// transposing stores and the row-wise loads free of bank conflicts.  Small tiles (32 KiB per CTA)
+// so that several CTAs per SM overlap their load and store phases.
+constexpr int kRevT = 5;
+
 struct BitRevArgs {
-  int m;            // qubits [0, m) are reversed, m >= 12
+  int m;            // qubits [0, m) are reversed, m >= 2 kRevT
   int n_local;
-  uint64_t n_work;  // 2^(n_local - 12): (outer bits above m) x (middle value)
+  uint64_t n_work;  // 2^(n_local - 2 kRevT): (outer bits above m) x (middle value)
 };
 
-__device__ __forceinline__ uint32_t rev6(uint32_t x) { return __brev(x) >> 26; }
-__device__ __forceinline__ uint32_t cobra_slot(uint32_t a, uint32_t c) {
-  const uint32_t row = rev6(c);
-  return row * 64u + ((a ^ (a >> 3) ^ ((row >> 2) & 7u)) & 63u);
+template <int T>
+__device__ __forceinline__ uint32_t rev_t(uint32_t x) { return __brev(x) >> (32 - T); }
+template <int T>
+__device__ __forceinline__ uint32_t cobra_col(uint32_t col, uint32_t row) {
+  return (col ^ (col >> 3) ^ ((row >> (T - 4)) & 7u)) & ((1u << T) - 1u);
 }
 
-static __global__ void __launch_bounds__(kTileThreads, 1) k_bit_reverse(amp* __restrict__ psi, const __grid_constant__ BitRevArgs A) {
+static __global__ void __launch_bounds__(kTileThreads, 4) k_bit_reverse(amp* __restrict__ psi, const __grid_constant__ BitRevArgs A) {
+  constexpr int T = kRevT;
+  constexpr uint32_t W = 1u << T;                      // tile is W x W
+  constexpr uint32_t ROWS_PER_IT = 2 * kTileThreads / W;  // each thread moves 2 adjacent amplitudes
+  constexpr uint32_t ITS = W / ROWS_PER_IT;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   amp* bufA = reinterpret_cast<amp*>(smem_raw);
-  amp* bufB = bufA + 4096;
-  const int mid_bits = A.m - 12;
+  amp* bufB = bufA + W * W;
+  const int mid_bits = A.m - 2 * T;
   const uint32_t tid = threadIdx.x;
-  const uint32_t c2 = (tid & 31u) * 2u, a_lo = tid >> 5;  // this thread's column pair and row within an 8-row slab
+  const uint32_t c2 = (tid % (W / 2)) * 2u, a_lo = tid / (W / 2);
+  const int hi = A.m - T;  // position of the `a` field
   for (uint64_t w = blockIdx.x; w < A.n_work; w += gridDim.x) {
-    const uint64_t u = w & ((1ULL << mid_bits) - 1ULL);
+    const uint64_t u = mid_bits ? (w & ((1ULL << mid_bits) - 1ULL)) : 0ULL;
     const uint64_t o = w >> mid_bits;
     const uint64_t ur = mid_bits ? (__brevll(u) >> (64 - mid_bits)) : 0ULL;
     if (u > ur) continue;  // the pair is handled by the CTA that drew the smaller middle value
-    const uint64_t base_u = (o << A.m) | (u << 6), base_r = (o << A.m) | (ur << 6);
-    const int hi = A.m - 6;  // position of the `a` field
-    amp2 x[8], y[8];
+    const uint64_t base_u = (o << A.m) | (u << T), base_r = (o << A.m) | (ur << T);
+    amp2 x[ITS], y[ITS];
 #pragma unroll
-    for (uint32_t it = 0; it < 8; ++it) x[it] = ld_amp2(psi + (base_u | ((uint64_t)(it * 8u + a_lo) << hi) | c2));
+    for (uint32_t it = 0; it < ITS; ++it) x[it] = ld_amp2(psi + (base_u | ((uint64_t)(it * ROWS_PER_IT + a_lo) << hi) | c2));
     if (u != ur) {
 #pragma unroll
-      for (uint32_t it = 0; it < 8; ++it) y[it] = ld_amp2(psi + (base_r | ((uint64_t)(it * 8u + a_lo) << hi) | c2));
+      for (uint32_t it = 0; it < ITS; ++it) y[it] = ld_amp2(psi + (base_r | ((uint64_t)(it * ROWS_PER_IT + a_lo) << hi) | c2));
     }
+    // element (a, c) -> row revT(c), swizzled column a
+    const uint32_t r0 = rev_t<T>(c2), r1 = r0 | (W >> 1);
 #pragma unroll
-    for (uint32_t it = 0; it < 8; ++it) {
-      const uint32_t a = it * 8u + a_lo;
-      bufA[cobra_slot(a, c2)] = x[it].a;
-      bufA[cobra_slot(a, c2 + 1u)] = x[it].b;
+    for (uint32_t it = 0; it < ITS; ++it) {
+      const uint32_t a = it * ROWS_PER_IT + a_lo;
+      const uint32_t s0 = r0 * W + cobra_col<T>(a, r0), s1 = r1 * W + cobra_col<T>(a, r1);
+      bufA[s0] = x[it].a;
+      bufA[s1] = x[it].b;
       if (u != ur) {
-        bufB[cobra_slot(a, c2)] = y[it].a;
-        bufB[cobra_slot(a, c2 + 1u)] = y[it].b;
+        bufB[s0] = y[it].a;
+        bufB[s1] = y[it].b;
       }
     }
     __syncthreads();
-    // output element (a', c') of the tile at rev(u) is input element (rev6 c', rev6 a') of the tile at u:
-    // slot row = rev6(rev6 a') = a', column from a = rev6(c')
+    // output element (a', c') of the tile at rev(u) is input element (revT c', revT a') of the tile at u:
+    // row = a', column from a = revT(c')
 #pragma unroll
-    for (uint32_t it = 0; it < 8; ++it) {
-      const uint32_t ap = it * 8u + a_lo;
-      const uint32_t sw = (ap >> 2) & 7u;
-      const uint32_t col0 = rev6(c2), col1 = col0 | 32u;
-      const uint32_t s0 = ap * 64u + ((col0 ^ (col0 >> 3) ^ sw) & 63u), s1 = ap * 64u + ((col1 ^ (col1 >> 3) ^ sw) & 63u);
+    for (uint32_t it = 0; it < ITS; ++it) {
+      const uint32_t ap = it * ROWS_PER_IT + a_lo;
+      const uint32_t s0 = ap * W + cobra_col<T>(r0, ap), s1 = ap * W + cobra_col<T>(r1, ap);
       amp2 v;
       v.a = bufA[s0];
       v.b = bufA[s1];
