@@ -13,5 +13,6 @@ ncu --metrics $M --clock-control none -c 400 --csv --log-file $O/r01_launches_qf
 ncu --set full --import-source on --clock-control none -k regex:k_tile_pass -s 4 -c 1 -o $O/r01_k_tile_pass_30q python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-kernel-sweep > /dev/null 2>&1
 ncu --set full --import-source on --clock-control none -k regex:k_qft_pass -s 2 -c 1 -o $O/r01_k_qft_pass_30q python bench.py --workload qft --steps 1 --warmup 1 --no-cpu-baseline --no-kernel-sweep > /dev/null 2>&1
 ncu --set full --import-source on --clock-control none -k regex:k_pair_v2 -s 3 -c 1 -o $O/r01_k_pair_v2_30q python bench.py --fusion 0 --steps 1 --warmup 1 --no-cpu-baseline --no-kernel-sweep > /dev/null 2>&1
+ncu --set full --import-source on --clock-control none -k regex:k_bit_reverse -s 1 -c 1 -o $O/r01_k_bit_reverse_30q python bench.py --workload qft --steps 1 --warmup 1 --no-cpu-baseline --no-kernel-sweep > /dev/null 2>&1
 python bench.py --impl reference > $O/r01_bench_reference.json 2> $O/r01_bench_reference.err; cut -c1-300 $O/r01_bench_reference.json
 ls -la $O | tail -20

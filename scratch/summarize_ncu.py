@@ -32,7 +32,7 @@ for name,f in (("random circuit (BASELINE config 2)","r01_launches_random.csv"),
     if "random" in f and "k_tile_pass" in agg: a=agg["k_tile_pass"]; traffic["random:30"]={"kernel":"k_tile_pass","dram_bytes_per_launch":int((a["rd"]+a["wr"])/a["n"]),"algorithmic_bytes_per_launch":32<<30}
     if "qft" in f and "k_qft_pass" in agg: a=agg["k_qft_pass"]; traffic["qft:30"]={"kernel":"k_qft_pass","dram_bytes_per_launch":int((a["rd"]+a["wr"])/a["n"]),"algorithmic_bytes_per_launch":32<<30}
 json.dump(traffic, open(os.path.join(P,"r01_traffic.json"),"w"), indent=1)
-for title,f in (("k_tile_pass (fused gate block), one launch","r01_k_tile_pass_30q.ncu-rep"),("k_qft_pass (radix-8 QFT pass), one launch","r01_k_qft_pass_30q.ncu-rep"),("k_pair_v2 (single 1-qubit gate, unfused), one launch","r01_k_pair_v2_30q.ncu-rep")):
+for title,f in (("k_tile_pass (fused gate block), one launch","r01_k_tile_pass_30q.ncu-rep"),("k_qft_pass (radix-8 QFT pass), one launch","r01_k_qft_pass_30q.ncu-rep"),("k_bit_reverse (one-pass qubit reversal), one launch","r01_k_bit_reverse_30q.ncu-rep"),("k_pair_v2 (single gate, unfused), one launch","r01_k_pair_v2_30q.ncu-rep")):
     m=full(os.path.join(O,f),KEYS)
     md += [f"## `ncu --set full` — {title}","","| metric | value | unit |","|---|---|---|"]
     for k,(v,u) in m.items():
