@@ -260,6 +260,91 @@ inline std::vector<RoundPlan> schedule_rounds(const std::vector<Op>& all, const 
   return rounds;
 }
 
+// ---- round matrices ---------------------------------------------------------------------------------
+// Applies `op` to the 8 amplitudes spanned by a round's bits.  rpos[q] = register bit of qubit q
+// (-1: not a round qubit, then vval[q] is its value for this matrix variant).
+inline void apply_small(const Op& op, const int* rpos, const int* vval, cplx* vec) {
+  uint32_t cmask = 0;
+  for (int i = 0; i < op.n_ctrl; ++i) {
+    const int q = op.ctrl[i];
+    if (rpos[q] >= 0) cmask |= 1u << rpos[q];
+    else if (!vval[q]) return;  // this variant has the control at 0: identity
+  }
+  auto live = [&](uint32_t x) { return (x & cmask) == cmask; };
+  switch (op.kind) {
+    case OP_PAIR: {
+      const uint32_t b0 = 1u << rpos[op.tgt[0]];
+      const uint32_t b1 = op.n_tgt == 2 ? 1u << rpos[op.tgt[1]] : 0u;
+      for (uint32_t x = 0; x < 8; ++x) {
+        if ((x & (b0 | b1)) || !live(x)) continue;
+        const uint32_t ia = op.n_tgt == 1 ? x : (x | b0), ib = op.n_tgt == 1 ? (x | b0) : (x | b1);
+        const cplx a = vec[ia], b = vec[ib];
+        vec[ia] = op.m[0] * a + op.m[1] * b;
+        vec[ib] = op.m[2] * a + op.m[3] * b;
+      }
+      break;
+    }
+    case OP_DENSE2:
+    case OP_DENSE3: {
+      const int nt = op.kind == OP_DENSE2 ? 2 : 3, d = 1 << nt;
+      uint32_t tm = 0, off[8];
+      for (int j = 0; j < nt; ++j) tm |= 1u << rpos[op.tgt[j]];
+      for (int c = 0; c < d; ++c) {
+        off[c] = 0;
+        for (int j = 0; j < nt; ++j)
+          if ((c >> j) & 1) off[c] |= 1u << rpos[op.tgt[j]];
+      }
+      for (uint32_t x = 0; x < 8; ++x) {
+        if ((x & tm) || !live(x)) continue;
+        cplx in[8], out[8];
+        for (int c = 0; c < d; ++c) in[c] = vec[x | off[c]];
+        for (int r = 0; r < d; ++r) {
+          cplx acc = op.m[r * d] * in[0];
+          for (int c = 1; c < d; ++c) acc += op.m[r * d + c] * in[c];
+          out[r] = acc;
+        }
+        for (int c = 0; c < d; ++c) vec[x | off[c]] = out[c];
+      }
+      break;
+    }
+    case OP_DIAG:
+      for (uint32_t x = 0; x < 8; ++x) {
+        if (!live(x)) continue;
+        int idx = 0;
+        for (int s = 0; s < op.n_tgt; ++s) {
+          const int q = op.tgt[s];
+          const int bit = rpos[q] >= 0 ? (int)((x >> rpos[q]) & 1u) : vval[q];
+          idx |= bit << s;
+        }
+        vec[x] *= op.m[idx];
+      }
+      break;
+    default: break;
+  }
+}
+
+// The 2^v matrices of a round (v = rp.vq.size()): matrix a is the product, in program order, of the
+// round's ops with the variant qubits fixed to the bits of a.  Row-major 8x8, register bit j of the
+// row/column index <-> tile bit rp.rbits[j].  `out` holds 64 << v entries.
+inline void build_round_matrices(const std::vector<Op>& all, const PassPlan& plan, const RoundPlan& rp, cplx* out) {
+  int rpos[64];
+  for (int q = 0; q < 64; ++q) rpos[q] = -1;
+  for (int j = 0; j < 3; ++j) rpos[plan.tile[rp.rbits[j]]] = j;
+  const int nv = (int)rp.vq.size();
+  for (int a = 0; a < (1 << nv); ++a) {
+    int vval[64];
+    for (int q = 0; q < 64; ++q) vval[q] = 0;
+    for (int j = 0; j < nv; ++j) vval[rp.vq[j]] = (a >> j) & 1;
+    cplx* M = out + (size_t)a * 64;
+    for (int col = 0; col < 8; ++col) {
+      cplx vec[8];
+      for (int x = 0; x < 8; ++x) vec[x] = cplx(x == col ? 1.0 : 0.0, 0.0);
+      for (int idx : rp.ops) apply_small(all[idx], rpos, vval, vec);
+      for (int row = 0; row < 8; ++row) M[row * 8 + col] = vec[row];
+    }
+  }
+}
+
 // ---- QFT recognition ---------------------------------------------------------------------------------
 // QCSim's own QuantumFourierTransform (QuantumFourierTransform.h:35-87) reaches the engine as a
 // stream of H / ControlledPhaseShift / SWAP gates.  The exact stream -- same order, the reference's

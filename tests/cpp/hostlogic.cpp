@@ -143,3 +143,33 @@ int hl_rounds(const qcsim_gate* gates, int count, unsigned long long tile_mask, 
   return (int)rounds.size();
 }
 }
+
+// ---- round matrices of a fused pass (planner.h: build_round_matrices) ----------------------------
+extern "C" {
+// Same planning as hl_rounds; additionally writes, round after round, the 2^nvar 8x8 matrices
+// (row-major, re/im pairs) into `mats` (capacity max_mats matrices).  Returns the number of rounds,
+// or -1 if `mats` is too small.
+int hl_round_matrices(const qcsim_gate* gates, int count, unsigned long long tile_mask, int max_var, int* rbits, int* nvar,
+                      int* vq, double* mats, int max_mats) {
+  std::vector<Op> ops;
+  PassPlan plan;
+  for (int q = 0; q < 64; ++q)
+    if ((tile_mask >> q) & 1ULL) plan.tile.push_back(q);
+  for (int i = 0; i < count; ++i) {
+    ops.push_back(classify(gates[i].nq, gates[i].m, gates[i].flags, gates[i].q, gates[i].c1, gates[i].c2));
+    if (ops.back().kind != OP_NOP) plan.ops.push_back(i);
+  }
+  const std::vector<RoundPlan> rounds = schedule_rounds(ops, plan, max_var);
+  int used = 0;
+  for (size_t r = 0; r < rounds.size(); ++r) {
+    const int nv = (int)rounds[r].vq.size();
+    if (used + (1 << nv) > max_mats) return -1;
+    for (int j = 0; j < 3; ++j) rbits[3 * r + j] = rounds[r].rbits[j];
+    nvar[r] = nv;
+    for (int j = 0; j < 3; ++j) vq[3 * r + j] = j < nv ? rounds[r].vq[j] : -1;
+    build_round_matrices(ops, plan, rounds[r], reinterpret_cast<cplx*>(mats) + (size_t)used * 64);
+    used += 1 << nv;
+  }
+  return (int)rounds.size();
+}
+}

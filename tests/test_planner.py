@@ -254,3 +254,66 @@ def test_round_scheduler_invariants(hl, seed):
     for i in flat:
         b = apply_op(b, ops[i], n)
     assert np.max(np.abs(a - b)) < 1e-13
+
+
+@pytest.mark.parametrize("seed,tile", [(1, 0xFFF), (2, 0x3F0F), (3, 0xFFF)])
+def test_round_matrices_reproduce_the_circuit(hl, seed, tile):
+    """What k_tile_pass computes, emulated in numpy: for every round, every amplitude group is
+    multiplied by the 8x8 matrix selected by its variant bits.  The product over the rounds must equal
+    the gate-by-gate circuit -- this pins schedule_rounds + build_round_matrices (all gate kinds,
+    controls inside / outside the round, diagonal selectors) without a GPU."""
+    n = 14
+    tq = [q for q in range(n) if (tile >> q) & 1]
+    rng = np.random.default_rng(seed)
+    # gates whose non-diagonal targets lie in the tile; controls / selectors anywhere
+    circ = []
+    samples = gates.all_gate_samples()
+    while len(circ) < 60:
+        g = samples[int(rng.integers(0, len(samples)))]
+        qs = [int(x) for x in rng.permutation(n)[:3]]
+        gg = g if rng.integers(0, 2) else gates.AppliedGate(g.matrix)
+        circ.append((gg, qs[0], qs[1] if g.nq > 1 else 0, qs[2] if g.nq > 2 else 0))
+    arr = pack(circ)
+    N = len(circ)
+    ops = (HlOp * N)()
+    keep = []
+    for i in range(N):
+        hl.hl_classify(C.byref(arr, i * C.sizeof(_lib.GateStruct)), C.byref(ops[i]))
+        op = ops[i]
+        nd = [op.tgt[j] for j in range(op.n_tgt)] if op.kind != OP_DIAG else []
+        if all(q in tq for q in nd):
+            keep.append(i)
+    circ = [circ[i] for i in keep]
+    arr = pack(circ)
+    N = len(circ)
+    assert N > 20
+    R = N + 4
+    rbits, nvar, vq = (C.c_int * (3 * R))(), (C.c_int * R)(), (C.c_int * (3 * R))()
+    max_mats = 8 * R
+    mats = (C.c_double * (128 * max_mats))()
+    hl.hl_round_matrices.restype = C.c_int
+    nr = hl.hl_round_matrices(arr, N, tile, 3, rbits, nvar, vq, mats, max_mats)
+    assert 0 < nr < N
+    M = np.frombuffer(mats, dtype=np.complex128).reshape(max_mats, 8, 8)
+    psi = random_state(n, 5)
+    want = psi.copy()
+    for g, q, c1, c2 in circ:
+        want = full_matrix_apply(want, g, [q, c1, c2], n)
+    got = psi.copy()
+    idx = np.arange(1 << n)
+    used = 0
+    for r in range(nr):
+        rq = [tq[rbits[3 * r + j]] for j in range(3)]          # register bit j <-> qubit
+        var = [vq[3 * r + j] for j in range(nvar[r])]
+        tm = sum(1 << q for q in rq)
+        base = idx[(idx & tm) == 0]
+        offs = [sum((1 << rq[j]) for j in range(3) if (x >> j) & 1) for x in range(8)]
+        vin = np.stack([got[base | o] for o in offs])            # 8 x groups
+        vidx = np.zeros(base.shape, dtype=int)
+        for j, q in enumerate(var):
+            vidx |= ((base >> q) & 1) << j
+        vout = np.einsum("gij,jg->ig", M[used + vidx], vin)
+        for x, o in enumerate(offs):
+            got[base | o] = vout[x]
+        used += 1 << nvar[r]
+    assert np.max(np.abs(got - want)) < 1e-13
