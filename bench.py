@@ -401,6 +401,17 @@ def _stratified_sample(layer, k):
     return [layer[int(i * step)] for i in range(k)]
 
 
+def _use_all_host_threads(sim):
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arms use every core this process may run on."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    if hasattr(sim, "set_num_threads"):
+        sim.set_num_threads(max(1, n))
+    return sim.num_threads()
+
+
 def cpu_baseline(n_target, workload, budget_s=20.0, variant="avx2"):
     import oracle
 
@@ -411,7 +422,7 @@ def cpu_baseline(n_target, workload, budget_s=20.0, variant="avx2"):
     if not oracle.ref_available(variant):
         variant = "sse2"
     sim = oracle.best_oracle(n, variant)
-    threads = sim.num_threads()
+    threads = _use_all_host_threads(sim)
     layers = make_layers(n, 4, workload)
     sample = _stratified_sample(layers[0], 11) if workload == "random" else layers[0][:: max(1, len(layers[0]) // 24)]
     sim.apply(*sample[0])  # warm-up / first touch
@@ -449,6 +460,7 @@ def run_reference(args):
     # calibrate at a small size, then choose (n, gates per step) so K + W steps fit ~150 s
     budget = 150.0
     with oracle.best_oracle(22, variant) as cal:
+        _use_all_host_threads(cal)
         lay = make_layers(22, 1, args.workload)[0]
         smp = _stratified_sample(lay, 11)
         cal.apply(*smp[0])
@@ -460,7 +472,7 @@ def run_reference(args):
         n -= 1
     gates_per_step = int(max(1, min(11, budget / ((K + W) * per_gate_22 * 2.0 ** (n - 22)))))
     sim = oracle.best_oracle(n, variant)
-    threads = sim.num_threads()
+    threads = _use_all_host_threads(sim)
     layers = make_layers(n, K + W, args.workload)
     samples = [_stratified_sample(l, gates_per_step) for l in layers]
     for i in range(W):
