@@ -7,10 +7,13 @@
 
 namespace qcsim {
 
-// Execute `ops` in order on the register.  Consecutive ops whose non-diagonal targets fit in one
-// shared-memory tile are applied in a single pass over HBM; everything else runs as single-gate
-// kernels.  Result is identical (to rounding) to applying the ops one by one.
+// Execute `ops` in order on the register.  QFT / IQFT gate streams are recognised and run as
+// radix-8 passes (qft_kernels.cuh); of the rest, ops whose non-diagonal targets fit in one
+// shared-memory tile are applied in a single pass over HBM (tile_kernels.cuh) and everything else
+// runs as single-gate kernels.  Result is identical (to rounding) to applying the ops one by one.
 int fusion_execute(qcsim_sv* h, const std::vector<Op>& ops);
+// same; a trailing run of ops that is still a valid QFT prefix is returned in `deferred` instead of
+// being executed (used when the bounded gate queue is flushed while a transform is still arriving)
 int fusion_execute_partial(qcsim_sv* h, const std::vector<Op>& ops, std::vector<Op>* deferred);
 
 // same, for ops whose qubit indices are already physical bit positions of the local slice
