@@ -108,7 +108,7 @@ namespace QC {
 
 		QubitRegister(QubitRegister&& o) noexcept
 			: NrQubits(o.NrQubits), NrBasisStates(o.NrBasisStates), handle(o.handle), mirror(std::move(o.mirror)), mirrorValid(o.mirrorValid),
-			rng(o.rng), uniformZeroOne(0, 1), computeGates(std::move(o.computeGates)), recordGates(o.recordGates)
+			registerStorage{ this }, rng(o.rng), uniformZeroOne(0, 1), computeGates(std::move(o.computeGates)), recordGates(o.recordGates)
 		{
 			o.handle = nullptr;
 		}
@@ -567,6 +567,18 @@ namespace QC {
 		qcsim_sv* handle = nullptr;       // replaces registerStorage / resultsStorage / savedStateStorage (:718-721)
 		mutable VectorClass mirror;       // host copy handed out by getRegisterStorage()
 		mutable bool mirrorValid = false;
+
+		// QCSim's own QubitRegisterDebug.h reads the protected member `registerStorage(i)` (QubitRegisterDebug.h:30-34).
+		// Here the storage is on the device, so the name is a small read-only proxy onto the host mirror: the
+		// reference header compiles against this class unchanged.
+		struct StorageProxy
+		{
+			const QubitRegister* owner;
+			std::complex<double> operator()(size_t i) const { return owner->getRegisterStorage()(i); }
+			std::complex<double> operator[](size_t i) const { return owner->getRegisterStorage()(i); }
+			size_t size() const { return owner->NrBasisStates; }
+		};
+		StorageProxy registerStorage{ this };
 
 		std::mt19937_64 rng;
 		std::uniform_real_distribution<double> uniformZeroOne;

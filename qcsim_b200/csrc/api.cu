@@ -76,7 +76,7 @@ int qcsim_sv_clone(const qcsim_sv* src, qcsim_sv** out) {
 int qcsim_sv_sync(qcsim_sv* h) {
   API_GUARD(h);
   QCSIM_TRY(engine_flush(h));
-  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  QCSIM_TRY(engine_wait(h));
   return QCSIM_OK;
 }
 
@@ -179,7 +179,8 @@ int qcsim_sv_save_state(qcsim_sv* h) {
 
 int qcsim_sv_restore_state(qcsim_sv* h, int destructive) {
   API_GUARD(h);
-  engine_drop_queue(h);
+  if (!h->saved) return QCSIM_OK;  // nothing saved: the reference leaves the register alone (QubitRegister.h:607,613); queued gates stay queued
+  engine_drop_queue(h);            // the restored state overwrites whatever the queued gates would have produced
   return engine_restore(h, destructive != 0);
 }
 

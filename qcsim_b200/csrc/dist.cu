@@ -13,8 +13,10 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 
 #include "dist.h"
 #include "dist_plan.h"
@@ -55,6 +57,12 @@ struct DistState {
   // peer-memory path: every rank's slice mapped into this process through CUDA IPC
   bool p2p = false;
   amp* peer_psi[64] = {};
+  // SPMD discipline: every rank must make the same collective-bearing calls in the same order.
+  // seq_hash folds (kind, arguments) of each such call; with QCSIM_SPMD_CHECK=1 the hashes are
+  // compared across ranks before every collective and a mismatch is an error instead of a hang.
+  uint64_t seq_hash = 0x9e3779b97f4a7c15ULL;
+  uint64_t seq_count = 0;
+  bool broken = false;  // a collective timed out / mismatched: the communicator was aborted
 };
 
 DistState* st(qcsim_sv* h) { return static_cast<DistState*>(h->dist); }
@@ -65,7 +73,83 @@ int log2i(int w) {
   return l;
 }
 
+int env_flag(const char* name) {
+  const char* s = std::getenv(name);
+  return s ? std::atoi(s) : 0;
+}
+
+double collective_timeout_s() {
+  static const double v = [] {
+    const char* s = std::getenv("QCSIM_COLLECTIVE_TIMEOUT_S");
+    const double t = s ? std::atof(s) : 300.0;
+    return t > 0 ? t : 300.0;
+  }();
+  return v;
+}
+
 }  // namespace
+
+// Bounded wait: a stream that holds a collective whose peers never arrive (SPMD violation: the ranks
+// made different calls) would otherwise spin forever inside NCCL.
+int dist_wait(qcsim_sv* h) {
+  DistState* d = st(h);
+  if (d && d->broken) return fail(QCSIM_ERR_NCCL, "sharded register is unusable after a failed collective");
+  const auto t0 = std::chrono::steady_clock::now();
+  int spins = 0;
+  for (;;) {
+    const cudaError_t ce = cudaStreamQuery(h->stream);
+    if (ce == cudaSuccess) return QCSIM_OK;
+    if (ce != cudaErrorNotReady) return fail(QCSIM_ERR_CUDA, "stream: %s", cudaGetErrorString(ce));
+    if (++spins > 2000) std::this_thread::sleep_for(std::chrono::microseconds(50));
+    if ((spins & 1023) == 0) {
+      const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      if (el > collective_timeout_s()) {
+        if (d && d->comm) {
+          ncclCommAbort(d->comm);
+          d->comm = nullptr;
+          h->nccl_comm = nullptr;
+          d->broken = true;
+        }
+        return fail(QCSIM_ERR_NCCL,
+                    "collective did not complete within %.0f s on rank %d after %llu collective calls: the ranks of a sharded "
+                    "register must make the same calls in the same order (SPMD); set QCSIM_SPMD_CHECK=1 to locate the mismatch",
+                    collective_timeout_s(), h->rank, (unsigned long long)(d ? d->seq_count : 0));
+      }
+    }
+  }
+}
+
+// Folds one collective-bearing call into the sequence hash; in check mode compares it across ranks first.
+static int spmd_note(qcsim_sv* h, uint64_t kind, uint64_t a = 0, uint64_t b = 0) {
+  DistState* d = st(h);
+  if (d->broken || !d->comm) return fail(QCSIM_ERR_NCCL, "sharded register is unusable after a failed collective");
+  auto mix = [](uint64_t x, uint64_t y) {
+    x ^= y + 0x9e3779b97f4a7c15ULL + (x << 6) + (x >> 2);
+    x *= 0xff51afd7ed558ccdULL;
+    return x ^ (x >> 33);
+  };
+  d->seq_hash = mix(mix(mix(d->seq_hash, kind), a), b);
+  d->seq_count++;
+  static const int check = env_flag("QCSIM_SPMD_CHECK");
+  if (!check) return QCSIM_OK;
+  // all-gather (hash, count) as exact 26-bit pieces in doubles; region [208, 208 + 4 * world) of d_small
+  double mine[4] = {(double)(d->seq_hash & 0x3ffffffULL), (double)((d->seq_hash >> 26) & 0x3ffffffULL), (double)(d->seq_hash >> 52),
+                    (double)d->seq_count};
+  double all[4 * kMaxWorld];
+  double* slot = d->d_small + 208;
+  CUDA_TRY(cudaMemcpyAsync(slot + 4 * h->rank, mine, sizeof mine, cudaMemcpyHostToDevice, h->stream));
+  NCCL_TRY(ncclAllGather(slot + 4 * h->rank, slot, 4, ncclDouble, d->comm, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(all, slot, sizeof(double) * 4 * h->world, cudaMemcpyDeviceToHost, h->stream));
+  QCSIM_TRY(dist_wait(h));
+  for (int r = 0; r < h->world; ++r)
+    for (int j = 0; j < 4; ++j)
+      if (all[4 * r + j] != mine[j]) {
+        d->broken = true;
+        return fail(QCSIM_ERR_NCCL, "SPMD violation: collective call #%llu (kind %llu) on rank %d does not match rank %d",
+                    (unsigned long long)d->seq_count, (unsigned long long)kind, h->rank, r);
+      }
+  return QCSIM_OK;
+}
 
 static int setup_peers(qcsim_sv* h);
 static void close_peers(qcsim_sv* h);
@@ -97,7 +181,7 @@ int dist_init(qcsim_sv* h, const void* nccl_id) {
     CUDA_TRY(cudaEventCreateWithFlags(&d->ev_group[i], cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&d->ev_copy[i], cudaEventDisableTiming));
   }
-  CUDA_TRY(cudaMalloc(&d->d_small, 256 * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&d->d_small, 256 * sizeof(double)));  // [0,200): reductions, [200]: barrier token, [208,240): SPMD check
   CUDA_TRY(cudaMemset(d->d_small, 0, 256 * sizeof(double)));
   return setup_peers(h);
 }
@@ -150,11 +234,12 @@ void dist_map_mask(qcsim_sv* h, uint64_t mask, uint64_t want, uint64_t* pmask, u
 // sum over ranks of `count` host doubles (count <= 256)
 int dist_allreduce_host(qcsim_sv* h, double* vals, int count) {
   DistState* d = st(h);
-  if (count > 256) return fail(QCSIM_ERR_BAD_ARG, "internal: allreduce too large");
+  if (count > 200) return fail(QCSIM_ERR_BAD_ARG, "internal: allreduce too large");
+  QCSIM_TRY(spmd_note(h, 1, (uint64_t)count));
   CUDA_TRY(cudaMemcpyAsync(d->d_small, vals, count * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   NCCL_TRY(ncclAllReduce(d->d_small, d->d_small, count, ncclDouble, ncclSum, d->comm, h->stream));
   CUDA_TRY(cudaMemcpyAsync(vals, d->d_small, count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  QCSIM_TRY(engine_wait(h));
   return QCSIM_OK;
 }
 
@@ -162,7 +247,7 @@ int dist_allreduce_host(qcsim_sv* h, double* vals, int count) {
 static int allgather_host(qcsim_sv* h, const double* mine, int per, double* all) {
   double buf[256];
   const int total = per * h->world;
-  if (total > 256) return fail(QCSIM_ERR_BAD_ARG, "internal: allgather too large");
+  if (total > 200) return fail(QCSIM_ERR_BAD_ARG, "internal: allgather too large");
   for (int i = 0; i < total; ++i) buf[i] = 0.0;
   for (int i = 0; i < per; ++i) buf[h->rank * per + i] = mine[i];
   QCSIM_TRY(dist_allreduce_host(h, buf, total));
@@ -224,10 +309,11 @@ static void close_peers(qcsim_sv* h) {
 static int setup_peers(qcsim_sv* h) {
   DistState* d = st(h);
   close_peers(h);
+  QCSIM_TRY(spmd_note(h, 2));
   const char* mode = std::getenv("QCSIM_EXCHANGE");
   const bool want = !(mode && std::strcmp(mode, "nccl") == 0);
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-  if (h->world * 8 + 8 > 256) return fail(QCSIM_ERR_BAD_ARG, "internal: too many ranks for the handle exchange");
+  if (h->world * 8 + 8 > 200) return fail(QCSIM_ERR_BAD_ARG, "internal: too many ranks for the handle exchange");
   cudaIpcMemHandle_t mine_h;
   std::memset(&mine_h, 0, sizeof mine_h);
   double ok = want ? 1.0 : 0.0;
@@ -240,7 +326,7 @@ static int setup_peers(qcsim_sv* h) {
   NCCL_TRY(ncclAllGather(slot_mine, d->d_small, 8, ncclDouble, d->comm, h->stream));
   cudaIpcMemHandle_t all[64];
   CUDA_TRY(cudaMemcpyAsync(all, d->d_small, 64 * h->world, cudaMemcpyDeviceToHost, h->stream));
-  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  QCSIM_TRY(engine_wait(h));
   if (ok != 0.0) {
     for (int r = 0; r < h->world; ++r) {
       if (r == h->rank) {
@@ -279,7 +365,7 @@ static int stream_barrier(qcsim_sv* h) {  // stream-ordered barrier over all ran
 static int ensure_stage(qcsim_sv* h, uint64_t chunk, int peers) {
   DistState* d = st(h);
   if (d->stage && d->stage_chunk >= chunk && d->stage_peers >= peers) return QCSIM_OK;
-  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  QCSIM_TRY(engine_wait(h));
   CUDA_TRY(cudaStreamSynchronize(d->copy_stream));
   cudaFree(d->stage);
   d->stage = nullptr;
@@ -290,10 +376,32 @@ static int ensure_stage(qcsim_sv* h, uint64_t chunk, int peers) {
   return QCSIM_OK;
 }
 
+// Resolve the timings of exchanges that have finished (all of them when `wait`), so the event list stays short.
+static void harvest_timings(qcsim_sv* h, bool wait) {
+  DistState* d = st(h);
+  size_t keep = 0;
+  for (size_t i = 0; i < d->timed.size(); ++i) {
+    auto& p = d->timed[i];
+    const bool done = wait ? cudaEventSynchronize(p.second) == cudaSuccess : cudaEventQuery(p.second) == cudaSuccess;
+    if (!done && !wait) {
+      d->timed[keep++] = p;
+      continue;
+    }
+    float ms = 0;
+    if (done && cudaEventElapsedTime(&ms, p.first, p.second) == cudaSuccess) h->stats.exchange_ms += ms;
+    cudaEventDestroy(p.first);
+    cudaEventDestroy(p.second);
+  }
+  d->timed.resize(keep);
+  cudaGetLastError();  // cudaEventQuery's cudaErrorNotReady is not an error
+}
+
 static int do_exchange(qcsim_sv* h, const DistStep& ex) {
   DistState* d = st(h);
   const int k = ex.k, nl = h->n_local;
   if (k < 1 || k > 3) return fail(QCSIM_ERR_BAD_ARG, "internal: bad exchange width");
+  QCSIM_TRY(spmd_note(h, 3, (uint64_t)k, (uint64_t)ex.gpos[0] | ((uint64_t)ex.gpos[1] << 8) | ((uint64_t)ex.gpos[2] << 16)));
+  harvest_timings(h, false);
   const uint64_t blk = h->dim_local >> k;  // amps per sub-block
   const uint64_t chunk = std::min<uint64_t>(blk, stage_chunk_amps());
   const int n_sub = 1 << k;
@@ -450,16 +558,8 @@ int dist_qft(qcsim_sv* h, int sq, int eq, bool do_swap, bool inverse, int* handl
 }
 
 void dist_collect_stats(qcsim_sv* h) {
-  DistState* d = st(h);
-  if (!d) return;
-  for (auto& p : d->timed) {
-    float ms = 0;
-    if (cudaEventSynchronize(p.second) == cudaSuccess && cudaEventElapsedTime(&ms, p.first, p.second) == cudaSuccess)
-      h->stats.exchange_ms += ms;
-    cudaEventDestroy(p.first);
-    cudaEventDestroy(p.second);
-  }
-  d->timed.clear();
+  if (!st(h)) return;
+  harvest_timings(h, true);
 }
 
 // ---- measurement scan over all ranks (layout is canonical here) -----------------------------------
@@ -473,7 +573,7 @@ int dist_pick_state(qcsim_sv* h, double prob, uint64_t fallback, uint64_t* outco
   k_find_chunk<<<1, 1024, 0, h->stream>>>(h->d_chunk_sums, h->n_chunks, dd_make(0, 0), 2.0, h->d_scan);  // prob 2: totals only
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpyAsync(res, h->d_scan, sizeof(ScanResult), cudaMemcpyDeviceToHost, h->stream));
-  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  QCSIM_TRY(engine_wait(h));
   h->stats.kernel_launches += 2;
   h->stats.state_passes += 1;
   h->stats.bytes_moved += 16ULL * h->dim_local;
@@ -487,7 +587,7 @@ int dist_pick_state(qcsim_sv* h, double prob, uint64_t fallback, uint64_t* outco
   k_find_in_chunk<<<1, kThreads, 0, h->stream>>>(h->psi, h->dim_local, prob, h->d_scan);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpyAsync(res, h->d_scan, sizeof(ScanResult), cudaMemcpyDeviceToHost, h->stream));
-  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  QCSIM_TRY(engine_wait(h));
   h->stats.kernel_launches += 2;
   double cand[2] = {res->found ? 1.0 : 0.0, res->found ? (double)(((uint64_t)h->rank << h->n_local) | res->index) : 0.0};
   QCSIM_TRY(allgather_host(h, cand, 2, all));
@@ -513,7 +613,7 @@ int dist_pick_state(qcsim_sv* h, double prob, uint64_t fallback, uint64_t* outco
         double* stage_acc = (double*)((char*)h->h_pinned + 1040);
         CUDA_TRY(cudaMemcpyAsync(stage, d_idx, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(cudaMemcpyAsync(stage_acc, h->d_scalars + 9, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        QCSIM_TRY(engine_wait(h));
         out[0] = (*stage == ~0ULL) ? 0.0 : (double)(*stage + 1);
         out[1] = *stage_acc;
       }

@@ -12,6 +12,7 @@ int dist_unique_id(void* out128);
 void dist_reset_layout(qcsim_sv* h);
 int dist_buffers_changed(qcsim_sv* h);
 void dist_map_mask(qcsim_sv* h, uint64_t mask, uint64_t want, uint64_t* pmask, uint64_t* pwant);
+int dist_wait(qcsim_sv* h);  // bounded wait for the stream (a collective whose peers never arrive must not hang the host)
 int dist_allreduce_host(qcsim_sv* h, double* vals, int count);
 int dist_apply(qcsim_sv* h, const Op& op);
 int dist_canonicalize(qcsim_sv* h);

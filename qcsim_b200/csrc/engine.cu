@@ -32,7 +32,24 @@ static inline void count_pass(qcsim_sv* h, uint64_t amps_touched, int launches =
 
 static inline amp to_amp(const cplx& z) { return make_amp(z.real(), z.imag()); }
 
+int engine_wait(qcsim_sv* h) {
+  if (h->world == 1) {
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return QCSIM_OK;
+  }
+  return dist_wait(h);
+}
+
 // ---- lifecycle ---------------------------------------------------------------------------------
+
+// cudaFuncSetAttribute is per device (context): called from engine_create after cudaSetDevice, so a
+// process that holds registers on several devices has it set on each of them
+int engine_init_device_kernels() {
+  CUDA_TRY(cudaFuncSetAttribute(k_qft_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 65 * 1024));
+  CUDA_TRY(cudaFuncSetAttribute(k_tile_permute, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  CUDA_TRY(cudaFuncSetAttribute(k_bit_reverse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * sizeof(amp) << (2 * kRevT))));
+  return QCSIM_OK;
+}
 
 int engine_create(qcsim_sv** out, int n_qubits, int device, int rank, int world, const void* nccl_id) {
   if (!out) return fail(QCSIM_ERR_BAD_ARG, "null output handle");
@@ -40,6 +57,7 @@ int engine_create(qcsim_sv** out, int n_qubits, int device, int rank, int world,
   if (n_qubits < 1 || n_qubits > 48) return fail(QCSIM_ERR_BAD_ARG, "n_qubits must be in 1..48");
   if (world < 1 || (world & (world - 1)) || rank < 0 || rank >= world)
     return fail(QCSIM_ERR_BAD_ARG, "world must be a power of two and 0 <= rank < world");
+  if (world > kMaxWorld) return fail(QCSIM_ERR_BAD_ARG, "at most %d shards (one NVSwitch domain) are supported", kMaxWorld);
   int log2w = 0;
   while ((1 << log2w) < world) ++log2w;
   if (n_qubits - log2w < 1) return fail(QCSIM_ERR_BAD_ARG, "too few qubits for this many shards");
@@ -50,6 +68,9 @@ int engine_create(qcsim_sv** out, int n_qubits, int device, int rank, int world,
                 ce == cudaSuccess ? "device count is 0" : cudaGetErrorString(ce));
   if (device < 0 || device >= ndev) return fail(QCSIM_ERR_BAD_ARG, "device %d out of range (%d devices)", device, ndev);
   CUDA_TRY(cudaSetDevice(device));
+  // opt-in shared-memory sizes are per device: set them for this device now (idempotent)
+  QCSIM_TRY(engine_init_device_kernels());
+  QCSIM_TRY(fusion_init_device_kernels());
 
   qcsim_sv* h = new qcsim_sv();
   h->n = n_qubits;
@@ -173,7 +194,7 @@ int engine_get_amplitude(qcsim_sv* h, uint64_t state, double* re_im) {
   stage[0] = stage[1] = 0;
   if ((state >> h->n_local) == (uint64_t)h->rank)
     CUDA_TRY(cudaMemcpyAsync(stage, h->psi + (state & (h->dim_local - 1)), sizeof(amp), cudaMemcpyDeviceToHost, h->stream));
-  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  QCSIM_TRY(engine_wait(h));
   if (h->world > 1) QCSIM_TRY(dist_allreduce_host(h, stage, 2));
   re_im[0] = stage[0];
   re_im[1] = stage[1];
@@ -192,7 +213,7 @@ int engine_transfer(qcsim_sv* h, double* host, uint64_t first, uint64_t count, b
     CUDA_TRY(cudaMemcpyAsync(d, host, count * sizeof(amp), cudaMemcpyHostToDevice, h->stream));
   else
     CUDA_TRY(cudaMemcpyAsync(host, d, count * sizeof(amp), cudaMemcpyDeviceToHost, h->stream));
-  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  QCSIM_TRY(engine_wait(h));
   return QCSIM_OK;
 }
 
@@ -210,7 +231,7 @@ int engine_masked_norm2(qcsim_sv* h, uint64_t mask, uint64_t want, double* out) 
   h->stats.bytes_moved += 16ULL * h->dim_local;
   double* stage = (double*)h->h_pinned;
   CUDA_TRY(cudaMemcpyAsync(stage, h->d_scalars, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  QCSIM_TRY(engine_wait(h));
   if (h->world > 1) QCSIM_TRY(dist_allreduce_host(h, stage, 1));
   *out = stage[0];
   return QCSIM_OK;
@@ -244,7 +265,7 @@ int engine_restore(qcsim_sv* h, bool destructive) {
   if (!h->saved) return QCSIM_OK;  // QubitRegister.h:607,613
   if (h->world > 1) dist_reset_layout(h);
   if (destructive) {
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    QCSIM_TRY(engine_wait(h));
     std::swap(h->psi, h->saved);
     CUDA_TRY(cudaFree(h->saved));
     h->saved = nullptr;
@@ -260,7 +281,7 @@ int engine_inner_product(qcsim_sv* a, qcsim_sv* b, double* re_im) {
     return fail(QCSIM_ERR_BAD_ARG, "registers must have the same shape and device");
   QCSIM_TRY(engine_canonicalize(a));
   QCSIM_TRY(engine_canonicalize(b));
-  CUDA_TRY(cudaStreamSynchronize(b->stream));
+  QCSIM_TRY(engine_wait(b));
   const int g = grid_for(a->dim_local);
   k_inner_product<<<g, kThreads, 0, a->stream>>>(a->psi, b->psi, a->dim_local, a->d_partials);
   k_final_sum<<<1, kThreads, 0, a->stream>>>(a->d_partials, g, 2, a->d_scalars);
@@ -268,7 +289,7 @@ int engine_inner_product(qcsim_sv* a, qcsim_sv* b, double* re_im) {
   a->stats.kernel_launches += 2;
   double* stage = (double*)a->h_pinned;
   CUDA_TRY(cudaMemcpyAsync(stage, a->d_scalars, 2 * sizeof(double), cudaMemcpyDeviceToHost, a->stream));
-  CUDA_TRY(cudaStreamSynchronize(a->stream));
+  QCSIM_TRY(engine_wait(a));
   if (a->world > 1) QCSIM_TRY(dist_allreduce_host(a, stage, 2));
   re_im[0] = stage[0];
   re_im[1] = stage[1];
@@ -487,12 +508,6 @@ int engine_qft_passes(qcsim_sv* h, int sq, int eq, bool inverse, uint64_t rank_b
     std::reverse(passes.begin(), passes.end());
     for (Pass& p : passes) std::reverse(p.groups.begin(), p.groups.end());
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(k_qft_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 65 * 1024));
-    CUDA_TRY(cudaFuncSetAttribute(k_tile_permute, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    attr_set = true;
-  }
   const double pi = 3.14159265358979323846;
   for (const Pass& p : passes) {
     QftPassArgs A;
@@ -560,11 +575,6 @@ int engine_permute_bits(qcsim_sv* h, const int* src_of) {
   if (swaps.empty()) return QCSIM_OK;
   const int Kmax = std::min(kMaxTileBits, nl);
   const uint64_t low = (1ULL << std::min(2, nl)) - 1ULL;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(k_tile_permute, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    attr_set = true;
-  }
   size_t i = 0;
   while (i < swaps.size()) {
     uint64_t bits = low;
@@ -731,7 +741,7 @@ int engine_pick_state(qcsim_sv* h, double prob, uint64_t fallback, uint64_t* out
   h->stats.bytes_moved += 16ULL * h->dim_local;
   ScanResult* res = (ScanResult*)h->h_pinned;
   CUDA_TRY(cudaMemcpyAsync(res, h->d_scan, sizeof(ScanResult), cudaMemcpyDeviceToHost, h->stream));
-  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  QCSIM_TRY(engine_wait(h));
   uint64_t s = res->found ? res->index : fallback;
   if (h->strict_measure) {
     // replay the reference's sequential fp64 sum (QubitRegister.h:172-190) for a bit-identical outcome
@@ -741,7 +751,7 @@ int engine_pick_state(qcsim_sv* h, double prob, uint64_t fallback, uint64_t* out
     h->stats.kernel_launches += 1;
     unsigned long long* stage = (unsigned long long*)((char*)h->h_pinned + 1024);
     CUDA_TRY(cudaMemcpyAsync(stage, d_idx, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    QCSIM_TRY(engine_wait(h));
     s = (*stage == ~0ULL) ? fallback : (uint64_t)*stage;
   }
   *outcome = s;

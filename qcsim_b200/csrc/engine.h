@@ -70,6 +70,13 @@ struct qcsim_sv {
 
 namespace qcsim {
 
+constexpr int kMaxWorld = 8;  // shards per register: one NVSwitch domain; exchange widths (dist_plan.h) are sized for log2 = 3
+int engine_init_device_kernels();
+int fusion_init_device_kernels();
+// Wait for the handle's stream.  On a sharded register the stream may hold a collective whose peers
+// never arrive (the ranks made different calls): the wait is bounded (QCSIM_COLLECTIVE_TIMEOUT_S,
+// default 300 s) and ends in QCSIM_ERR_NCCL instead of spinning.
+int engine_wait(qcsim_sv* h);
 int engine_create(qcsim_sv** out, int n_qubits, int device, int rank, int world, const void* nccl_id);
 int engine_nccl_unique_id(void* out128);
 int engine_destroy(qcsim_sv* h);

@@ -29,6 +29,11 @@ int env_int(const char* name, int dflt) {
 
 }  // namespace
 
+int fusion_init_device_kernels() {  // per device, from engine_create
+  CUDA_TRY(cudaFuncSetAttribute(k_tile_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (128 + 28) * 1024));
+  return QCSIM_OK;
+}
+
 // Build the round matrices + parameter block of one pass and launch it.  A launch holds at most
 // kMaxTileRounds rounds / kMaxTileMats matrices (parameter-block limit); a longer pass is cut into
 // several launches over the same tile set (each is still fp64-bound, not HBM-bound, at that length).
@@ -48,11 +53,6 @@ static int launch_pass(qcsim_sv* h, const std::vector<Op>& all, const PassPlan& 
   A.pipelined = pipe ? 1 : 0;
   const size_t tile_smem = ((size_t)sizeof(amp) << k) * (pipe ? 2 : 1);
   const size_t smem_max = tile_smem + (size_t)kMaxTileMats * kRoundMatAmps * sizeof(amp);
-  static bool attr_set = false;
-  if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(k_tile_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (128 + 28) * 1024));
-    attr_set = true;
-  }
   const int per_sm = pipe ? 1 : std::max(1, std::min(2, (int)((220 * 1024) / (smem_max + 1024))));
   const uint64_t grid = std::min<uint64_t>(A.n_tiles, (uint64_t)kNumSMs * per_sm);
   static const int debug = env_int("QCSIM_DEBUG_PLAN", 0);

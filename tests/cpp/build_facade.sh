@@ -3,10 +3,11 @@
 # where /root/reference exists (this container); the binaries travel to the GPU box.
 #
 # A quoted #include inside a QCSim header is resolved in that header's own directory first, so the
-# drop-in is done the way a maintainer would do it: QubitRegister.h and
-# QubitRegisterDebug.h are REPLACED in the QCSim source directory.  /root/reference is read-only,
-# so the replacement happens in a staging directory of symlinks (tests/cpp/_stage, git-ignored):
-# every QCSim header is linked as is, the two register headers point at qcsim_b200/cpp/.
+# drop-in is done the way a maintainer would do it: QubitRegister.h is REPLACED in
+# the QCSim source directory.  /root/reference is read-only, so the replacement happens in a staging
+# directory of symlinks (tests/cpp/_stage, git-ignored): every QCSim header is linked as is
+# (QubitRegisterDebug.h included: it compiles unchanged against the drop-in), QubitRegister.h points
+# at qcsim_b200/cpp/.
 set -e
 HERE="$(cd "$(dirname "$0")" && pwd)"
 ROOT="$(cd "$HERE/../.." && pwd)"
@@ -17,7 +18,6 @@ stage() {  # $1 = dir, $2 = 1 to also replace QuantumFourierTransform.h by the o
   for f in "$REF"/*.h; do ln -s "$f" "$1/$(basename "$f")"; done
   rm -f "$1/QubitRegisterCalculator.h"   # nothing may reach the CPU loops
   ln -sf "$ROOT/qcsim_b200/cpp/QubitRegister.h" "$1/QubitRegister.h"
-  ln -sf "$ROOT/qcsim_b200/cpp/QubitRegisterDebug.h" "$1/QubitRegisterDebug.h"
   if [ "$2" = 1 ]; then ln -sf "$ROOT/qcsim_b200/cpp/fast/QuantumFourierTransform.h" "$1/QuantumFourierTransform.h"; fi
 }
 stage "$HERE/_stage/plain" 0

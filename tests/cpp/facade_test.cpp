@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "QubitRegister.h"
+#include "QubitRegisterDebug.h"  // QCSim's own header, unchanged: reads the protected registerStorage(i)
 #include "QuantumFourierTransform.h"
 #include "GroverAlgorithm.h"
 #include "DraperAdder.h"
@@ -175,6 +176,17 @@ int main(int argc, char** argv) {
       auto hist = reg.RepeatedMeasure(50);
       std::printf("repeated %zu %zu\n", hist.size(), hist.count(1) ? hist[1] : 0);
       std::printf("threads_ok %d\n", TestRegister::GetNumberOfThreads() > 0);
+      {  // QCSim's QubitRegisterDebug (QubitRegisterDebug.h:20-43) on the drop-in register
+        QC::QubitRegisterDebug<Vec, Mat> dbg(3, 12345u);
+        dbg.ApplyGate(h, 1);
+        const std::string path = "/tmp/qcsim_b200_facade_debug.txt";
+        const bool ok = dbg.writeToFile(path, true, false);
+        std::ifstream in(path);
+        size_t idx = 0, lines = 0;
+        double val = 0, sumsq = 0;
+        while (in >> idx >> val) { ++lines; sumsq += val * val; }
+        std::printf("debug_dump %d %zu %.12f\n", ok ? 1 : 0, lines, sumsq);
+      }
     } else {
       return 1;
     }

@@ -144,3 +144,6 @@ def test_error_conventions_and_state_helpers():
     assert abs(re - 1 / np.sqrt(1.25)) < 1e-15 and abs(im) < 1e-15 and abs(im1 + 0.5 / np.sqrt(1.25)) < 1e-15
     assert out["repeated"][0].split()[0] in ("1", "2")
     assert out["threads_ok"][0] == "1"
+    # QCSim's own QubitRegisterDebug.h compiled unchanged on the drop-in: writeToFile dumps |amplitude| per basis state
+    ok, lines, sumsq = out["debug_dump"][0].split()
+    assert ok == "1" and int(lines) == 8 and abs(float(sumsq) - 1.0) < 1e-5
