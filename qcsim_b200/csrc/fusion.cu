@@ -14,9 +14,12 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <cudaTypedefs.h>
+
 #include "fusion.h"
 #include "planner.h"
 #include "tile_kernels.cuh"
+#include "tile_pipe.cuh"
 
 namespace qcsim {
 
@@ -29,8 +32,108 @@ int env_int(const char* name, int dflt) {
 
 }  // namespace
 
+constexpr size_t kPipeSmemBytes =
+    1024 /* alignment slack */ + (size_t)kPipeStages * kPipeTileBytes + (size_t)kMaxTileMats * kRoundMatAmps * sizeof(amp) +
+    2 * kPipeStages * sizeof(uint64_t);
+static_assert(kPipeSmemBytes <= 227 * 1024, "shared memory per CTA");
+
 int fusion_init_device_kernels() {  // per device, from engine_create
   CUDA_TRY(cudaFuncSetAttribute(k_tile_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (128 + 28) * 1024));
+  CUDA_TRY(cudaFuncSetAttribute(k_tile_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmemBytes));
+  return QCSIM_OK;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+static PFN_cuTensorMapEncodeTiled tensor_map_encoder() {
+  static PFN_cuTensorMapEncodeTiled fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<PFN_cuTensorMapEncodeTiled>(p);
+  }();
+  return fn;
+}
+
+// The TMA-staged, warp-specialised pass (tile_pipe.cuh).  Returns QCSIM_ERR_UNSUPPORTED when the tile
+// set has no TMA geometry (small registers), in which case the caller uses k_tile_pass.
+static int launch_pass_pipe(qcsim_sv* h, const std::vector<Op>& all, const PassPlan& plan_in) {
+  TmaTileGeom g;
+  if ((int)plan_in.tile.size() != kPipeTileBits || !tma_tile_geometry(plan_in.tile, h->n_local, &g)) return QCSIM_ERR_UNSUPPORTED;
+  PFN_cuTensorMapEncodeTiled encode = tensor_map_encoder();
+  if (!encode) return QCSIM_ERR_UNSUPPORTED;
+  const int k = kPipeTileBits;
+  // the tile in shared-memory slot order: everything downstream (round bits, item bits, variants) is in slot bits
+  PassPlan plan = plan_in;
+  for (int j = 0; j < k; ++j) plan.tile[j] = g.slot_qubit[j];
+  int local_of[64];
+  for (int q = 0; q < 64; ++q) local_of[q] = -1;
+  for (int j = 0; j < k; ++j) local_of[plan.tile[j]] = j;
+  const std::vector<RoundPlan> rplan = schedule_rounds(all, plan, kMaxVariantBits, /*swizzle_kind=*/1);
+
+  static thread_local PipePassArgs A;  // ~30 KiB: keep it off the stack; the launch copies it
+  {
+    cuuint64_t gdim[5], gstride[4];
+    cuuint32_t box[5], estride[5] = {1, 1, 1, 1, 1};
+    gdim[0] = 16;  // doubles: 8 amplitudes
+    box[0] = 16;
+    for (int d = 1; d < 5; ++d) {
+      gdim[d] = 1ULL << g.dim_bits[d];
+      box[d] = 1u << g.box_bits[d];
+      gstride[d - 1] = (cuuint64_t)sizeof(amp) << g.dim_lo[d];  // bytes between consecutive coordinates of dim d
+    }
+    const CUresult cr = encode(&A.tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, h->psi, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return fail(QCSIM_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
+  }
+  A.n_tiles = 1ULL << (h->n_local - k);
+  A.n_enum = g.n_enum;
+  A.box_bytes = (int)(sizeof(amp) << g.box_log2);
+  for (int d = 0; d < 5; ++d) {
+    A.dim_lo[d] = g.dim_lo[d];
+    A.dim_mask_bits[d] = g.dim_bits[d];
+  }
+  for (int j = 0; j < 9; ++j) A.enum_pos[j] = j < g.n_enum ? g.enum_pos[j] : 0;
+  for (int j = 0; j < k; ++j) {
+    A.sorted_pos[j] = plan_in.tile[j];
+    A.slot_pos[j] = g.slot_qubit[j];
+  }
+  const uint64_t grid = std::min<uint64_t>(A.n_tiles, (uint64_t)kNumSMs);
+  static const int debug = env_int("QCSIM_DEBUG_PLAN", 0);
+
+  size_t r = 0;
+  do {  // a pass without rounds cannot happen (plan_passes only fuses >= 2 ops), but the loop tolerates it
+    int n_rounds = 0;
+    size_t mat_index = 0, n_ops = 0;
+    while (r < rplan.size() && n_rounds < kMaxTileRounds && mat_index + ((size_t)1 << rplan[r].vq.size()) <= (size_t)kMaxTileMats) {
+      const RoundPlan& rp = rplan[r];
+      const int nv = (int)rp.vq.size();
+      build_round_matrices(all, plan, rp, reinterpret_cast<cplx*>(A.mats + mat_index * kRoundMatAmps));
+      const RoundDescHost hd = make_round_desc(rp, local_of, (uint32_t)mat_index);
+      TileRoundDesc& rd = A.rounds[n_rounds];
+      rd.rb = hd.rb;
+      for (int w = 0; w < 3; ++w) rd.tb[w] = hd.tb[w];
+      rd.var = hd.var;
+      rd.mat_off = hd.mat_off;
+      rd.pad[0] = rd.pad[1] = 0;
+      mat_index += (size_t)1 << nv;
+      n_ops += rp.ops.size();
+      ++n_rounds;
+      ++r;
+    }
+    A.n_rounds = n_rounds;
+    A.n_mats = (int)mat_index;
+    k_tile_pipe<<<(unsigned)grid, kPipeThreads, kPipeSmemBytes, h->stream>>>(A);
+    CUDA_TRY(cudaGetLastError());
+    h->stats.kernel_launches += 1;
+    h->stats.state_passes += 1;
+    h->stats.bytes_moved += 32ULL * h->dim_local;
+    h->stats.fused_rounds += n_rounds;
+    h->stats.fused_ops += n_ops;
+    if (debug > 1)
+      std::fprintf(stderr, "[qcsim pipe pass] box=2^%d amps x %d ops, ops=%zu rounds=%d matrices=%zu\n", g.box_log2, 1 << g.n_enum, n_ops,
+                   n_rounds, mat_index);
+  } while (r < rplan.size());
   return QCSIM_OK;
 }
 
@@ -66,17 +169,12 @@ static int launch_pass(qcsim_sv* h, const std::vector<Op>& all, const PassPlan& 
       const int nv = (int)rp.vq.size();
       // one 8x8 matrix per value of the variant qubits (planner.h), straight into the parameter block
       build_round_matrices(all, plan, rp, reinterpret_cast<cplx*>(A.mats + mat_index * kRoundMatAmps));
+      const RoundDescHost hd = make_round_desc(rp, local_of, (uint32_t)mat_index);
       TileRoundDesc& rd = A.rounds[n_rounds];
-      rd.rb = (uint32_t)(rp.rbits[0] | (rp.rbits[1] << 8) | (rp.rbits[2] << 16));
-      for (int w = 0; w < 3; ++w) rd.tb[w] = 0;
-      for (int j = 0; j < 9; ++j) rd.tb[j >> 2] |= (uint32_t)rp.item_bit[j] << (8 * (j & 3));
-      rd.var = (uint32_t)nv;
-      for (int j = 0; j < nv; ++j) {
-        const int q = rp.vq[j];
-        const uint32_t e = local_of[q] >= 0 ? (uint32_t)(local_of[q] << 1) : (uint32_t)((q << 1) | 1);
-        rd.var |= e << (8 + 8 * j);
-      }
-      rd.mat_off = (uint32_t)mat_index;
+      rd.rb = hd.rb;
+      for (int w = 0; w < 3; ++w) rd.tb[w] = hd.tb[w];
+      rd.var = hd.var;
+      rd.mat_off = hd.mat_off;
       rd.pad[0] = rd.pad[1] = 0;
       mat_index += (size_t)1 << nv;
       n_ops += rp.ops.size();
@@ -185,7 +283,11 @@ int fusion_execute_local(qcsim_sv* h, const std::vector<Op>& ops) {
       for (int idx : st.pass.ops) QCSIM_TRY(engine_launch_local(h, ops[idx]));
       continue;
     }
-    QCSIM_TRY(launch_pass(h, ops, st.pass, Lrun, rplan));
+    static const int legacy = env_int("QCSIM_TILE_LEGACY", 0);
+    int rc = QCSIM_ERR_UNSUPPORTED;
+    if (!legacy) rc = launch_pass_pipe(h, ops, st.pass);       // TMA-staged warp-specialised pass (tile_pipe.cuh)
+    if (rc == QCSIM_ERR_UNSUPPORTED) rc = launch_pass(h, ops, st.pass, Lrun, rplan);  // small registers: plain tile pass
+    QCSIM_TRY(rc);
   }
   return QCSIM_OK;
 }

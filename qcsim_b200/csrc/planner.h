@@ -142,7 +142,11 @@ struct RoundPlan {
   std::vector<int> ops;    // indices into the op list, program order
 };
 
-inline std::vector<RoundPlan> schedule_rounds(const std::vector<Op>& all, const PassPlan& plan, int max_variant_bits = 3) {
+// swizzle_kind selects the shared-memory slot swizzle the low item bits must dodge: 0 = swz() of
+// common.cuh (every tile bit folds onto the low three, class = bit mod 3), 1 = the 128 B TMA swizzle of
+// tile_pipe.cuh (only slot bits 3..5 fold onto 0..2).
+inline std::vector<RoundPlan> schedule_rounds(const std::vector<Op>& all, const PassPlan& plan, int max_variant_bits = 3,
+                                              int swizzle_kind = 0) {
   const int k = (int)plan.tile.size();
   int local_of[64];
   for (int q = 0; q < 64; ++q) local_of[q] = -1;
@@ -246,7 +250,7 @@ inline std::vector<RoundPlan> schedule_rounds(const std::vector<Op>& all, const 
     };
     for (int res = 0; res < 3; ++res)
       for (size_t i = 0; i < rest.size(); ++i)
-        if (rest[i] >= 0 && rest[i] % 3 == res) {
+        if (rest[i] >= 0 && rest[i] % 3 == res && (swizzle_kind == 0 || rest[i] < 6)) {
           order[next_free()] = rest[i];
           rest[i] = -1;
           break;
@@ -258,6 +262,88 @@ inline std::vector<RoundPlan> schedule_rounds(const std::vector<Op>& all, const 
     remaining.swap(left);
   }
   return rounds;
+}
+
+// ---- TMA tile geometry (tile_pipe.cuh) ---------------------------------------------------------------
+// The state vector seen as a rank-5 tensor of doubles whose dimensions are ranges of index bits:
+// dim 0 = bits [0,3) (8 amplitudes = 128 B, always boxed whole), dims 1.. = consecutive bit ranges
+// [lo_i, lo_{i+1}) whose LOW box_bits[i] bits are tile qubits (the TMA box spans them) and whose
+// remaining bits are addressed by the coordinate.  Tile qubits that no dimension boxes are
+// "enumerated": one TMA op per value.  The shared-memory slot order of the tile follows: qubits
+// 0..2, the boxed groups in dimension order, the enumerated qubits.
+struct TmaTileGeom {
+  int k = 0;
+  int slot_qubit[16];  // index bit held by shared-memory slot bit j
+  int n_dims = 0;      // dimensions in use (<= 5); the kernel always passes 5 coordinates
+  int dim_lo[5];
+  int dim_bits[5];     // log2 of the extent in amplitudes (dim 0: 3)
+  int box_bits[5];     // log2 of the box in amplitudes (dim 0: 3)
+  int n_enum = 0;
+  int enum_pos[16];
+  int box_log2 = 0;    // log2(amplitudes per TMA op)
+};
+
+// tile: ascending tile qubits.  Needs qubits 0,1,2 in the tile and at least 3 more.
+inline bool tma_tile_geometry(const std::vector<int>& tile, int n_local, TmaTileGeom* g) {
+  const int k = (int)tile.size();
+  if (k < 6 || k > 16 || n_local < k) return false;
+  for (int j = 0; j < 3; ++j)
+    if (tile[j] != j) return false;
+  struct Grp { int lo, w; };
+  std::vector<Grp> groups;  // contiguous runs of tile qubits >= 3, cut at width 8 (box extents are <= 256)
+  for (int j = 3; j < k; ++j) {
+    if (!groups.empty() && groups.back().lo + groups.back().w == tile[j] && groups.back().w < 8) ++groups.back().w;
+    else groups.push_back({tile[j], 1});
+  }
+  std::vector<Grp> boxed;
+  std::vector<char> taken(groups.size(), 0);
+  if (groups[0].lo == 3) {
+    boxed.push_back(groups[0]);
+    taken[0] = 1;
+  } else {
+    boxed.push_back({3, 0});  // dim 1 must start at bit 3; nothing of it is boxed
+  }
+  for (int pick = 0; pick < 3; ++pick) {  // up to three more groups, widest first
+    int best = -1;
+    for (size_t i = 0; i < groups.size(); ++i)
+      if (!taken[i] && (best < 0 || groups[i].w > groups[best].w)) best = (int)i;
+    if (best < 0) break;
+    taken[best] = 1;
+    boxed.push_back(groups[best]);
+  }
+  std::sort(boxed.begin(), boxed.end(), [](const Grp& a, const Grp& b) { return a.lo < b.lo; });
+  g->k = k;
+  g->n_dims = 1 + (int)boxed.size();
+  g->dim_lo[0] = 0;
+  g->dim_bits[0] = 3;
+  g->box_bits[0] = 3;
+  int ns = 0;
+  for (int j = 0; j < 3; ++j) g->slot_qubit[ns++] = j;
+  g->box_log2 = 3;
+  for (size_t i = 0; i < boxed.size(); ++i) {
+    const int hi = i + 1 < boxed.size() ? boxed[i + 1].lo : n_local;
+    g->dim_lo[1 + i] = boxed[i].lo;
+    g->dim_bits[1 + i] = hi - boxed[i].lo;
+    g->box_bits[1 + i] = boxed[i].w;
+    if (g->dim_bits[1 + i] < boxed[i].w || g->dim_bits[1 + i] > 31) return false;
+    for (int b = 0; b < boxed[i].w; ++b) g->slot_qubit[ns++] = boxed[i].lo + b;
+    g->box_log2 += boxed[i].w;
+  }
+  for (int d = g->n_dims; d < 5; ++d) {
+    g->dim_lo[d] = n_local;
+    g->dim_bits[d] = 0;
+    g->box_bits[d] = 0;
+  }
+  g->n_enum = 0;
+  for (size_t i = 0; i < groups.size(); ++i)
+    if (!taken[i])
+      for (int b = 0; b < groups[i].w; ++b) {
+        g->enum_pos[g->n_enum++] = groups[i].lo + b;
+        g->slot_qubit[ns++] = groups[i].lo + b;
+      }
+  if (ns != k || g->box_log2 + g->n_enum != k) return false;
+  if (g->box_log2 < 6) return false;  // every op must land on a 1024 B boundary (128 B swizzle atom = 8 rows)
+  return true;
 }
 
 // ---- round matrices ---------------------------------------------------------------------------------
@@ -343,6 +429,33 @@ inline void build_round_matrices(const std::vector<Op>& all, const PassPlan& pla
       for (int row = 0; row < 8; ++row) M[row * 8 + col] = vec[row];
     }
   }
+}
+
+// ---- round descriptor (what the tile kernels read per round) -----------------------------------------
+// Plain-integer image of TileRoundDesc (tile_kernels.cuh); built here so the CPU tests see exactly what
+// the kernels are given.
+struct RoundDescHost {
+  uint32_t rb;       // rb0 | rb1 << 8 | rb2 << 16 : tile bit held by register bit j
+  uint32_t tb[3];    // tile bit walked by item-index bit j, one byte each
+  uint32_t var;      // nvar | (src | pos << 1) << (8 + 8 j): src 0 = tile bit, 1 = index bit outside the tile
+  uint32_t mat_off;  // first matrix of the round
+};
+
+// local_of[q] = tile bit of qubit q (-1: outside the tile)
+inline RoundDescHost make_round_desc(const RoundPlan& rp, const int* local_of, uint32_t mat_index) {
+  RoundDescHost rd;
+  rd.rb = (uint32_t)(rp.rbits[0] | (rp.rbits[1] << 8) | (rp.rbits[2] << 16));
+  for (int w = 0; w < 3; ++w) rd.tb[w] = 0;
+  for (int j = 0; j < 9; ++j) rd.tb[j >> 2] |= (uint32_t)rp.item_bit[j] << (8 * (j & 3));
+  const int nv = (int)rp.vq.size();
+  rd.var = (uint32_t)nv;
+  for (int j = 0; j < nv; ++j) {
+    const int q = rp.vq[j];
+    const uint32_t e = local_of[q] >= 0 ? (uint32_t)(local_of[q] << 1) : (uint32_t)((q << 1) | 1);
+    rd.var |= e << (8 + 8 * j);
+  }
+  rd.mat_off = mat_index;
+  return rd;
 }
 
 // ---- QFT recognition ---------------------------------------------------------------------------------

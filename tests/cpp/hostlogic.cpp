@@ -173,3 +173,57 @@ int hl_round_matrices(const qcsim_gate* gates, int count, unsigned long long til
   return (int)rounds.size();
 }
 }
+
+// ---- TMA-staged pass (planner.h: tma_tile_geometry; fusion.cu: launch_pass_pipe) ------------------
+extern "C" {
+// geometry of a tile set: out = {n_dims, n_enum, box_log2, dim_lo[5], dim_bits[5], box_bits[5], enum_pos[9], slot_qubit[12]}
+int hl_tma_geometry(unsigned long long tile_mask, int n_local, int* out) {
+  std::vector<int> tile;
+  for (int q = 0; q < 64; ++q)
+    if ((tile_mask >> q) & 1ULL) tile.push_back(q);
+  TmaTileGeom g;
+  if (!tma_tile_geometry(tile, n_local, &g)) return 0;
+  int o = 0;
+  out[o++] = g.n_dims;
+  out[o++] = g.n_enum;
+  out[o++] = g.box_log2;
+  for (int d = 0; d < 5; ++d) out[o++] = g.dim_lo[d];
+  for (int d = 0; d < 5; ++d) out[o++] = g.dim_bits[d];
+  for (int d = 0; d < 5; ++d) out[o++] = g.box_bits[d];
+  for (int j = 0; j < 9; ++j) out[o++] = j < g.n_enum ? g.enum_pos[j] : 0;
+  for (int j = 0; j < 12; ++j) out[o++] = j < g.k ? g.slot_qubit[j] : 0;
+  return 1;
+}
+
+// Exactly what launch_pass_pipe hands to k_tile_pipe for ONE pass over `tile_mask` (12 qubits): the tile in
+// slot order, the rounds scheduled against the TMA swizzle, their descriptors (6 uint32 each: rb, tb[3], var,
+// mat_off) and matrices.  Returns the number of rounds, or -1.
+int hl_pipe_pass(const qcsim_gate* gates, int count, unsigned long long tile_mask, int n_local, unsigned* desc, double* mats, int max_mats) {
+  std::vector<Op> ops;
+  PassPlan plan;
+  for (int q = 0; q < 64; ++q)
+    if ((tile_mask >> q) & 1ULL) plan.tile.push_back(q);
+  for (int i = 0; i < count; ++i) {
+    ops.push_back(classify(gates[i].nq, gates[i].m, gates[i].flags, gates[i].q, gates[i].c1, gates[i].c2));
+    if (ops.back().kind != OP_NOP) plan.ops.push_back(i);
+  }
+  TmaTileGeom g;
+  if (!tma_tile_geometry(plan.tile, n_local, &g)) return -1;
+  for (int j = 0; j < g.k; ++j) plan.tile[j] = g.slot_qubit[j];
+  int local_of[64];
+  for (int q = 0; q < 64; ++q) local_of[q] = -1;
+  for (int j = 0; j < g.k; ++j) local_of[plan.tile[j]] = j;
+  const std::vector<RoundPlan> rounds = schedule_rounds(ops, plan, 3, 1);
+  int used = 0;
+  for (size_t r = 0; r < rounds.size(); ++r) {
+    const int nv = (int)rounds[r].vq.size();
+    if (used + (1 << nv) > max_mats) return -1;
+    build_round_matrices(ops, plan, rounds[r], reinterpret_cast<cplx*>(mats) + (size_t)used * 64);
+    const RoundDescHost rd = make_round_desc(rounds[r], local_of, (uint32_t)used);
+    unsigned* d = desc + 6 * r;
+    d[0] = rd.rb; d[1] = rd.tb[0]; d[2] = rd.tb[1]; d[3] = rd.tb[2]; d[4] = rd.var; d[5] = rd.mat_off;
+    used += 1 << nv;
+  }
+  return (int)rounds.size();
+}
+}

@@ -317,3 +317,176 @@ def test_round_matrices_reproduce_the_circuit(hl, seed, tile):
             got[base | o] = vout[x]
         used += 1 << nvar[r]
     assert np.max(np.abs(got - want)) < 1e-13
+
+
+# ---- TMA-staged pass (tile_pipe.cuh): geometry + the kernel's index arithmetic, emulated -------------------
+def _geometry(hl, tile_mask, n_local):
+    out = (C.c_int * 64)()
+    hl.hl_tma_geometry.restype = C.c_int
+    ok = hl.hl_tma_geometry(C.c_ulonglong(tile_mask), n_local, out)
+    if not ok:
+        return None
+    o = list(out)
+    g = {"n_dims": o[0], "n_enum": o[1], "box_log2": o[2], "dim_lo": o[3:8], "dim_bits": o[8:13], "box_bits": o[13:18],
+         "enum_pos": o[18:27][: o[1]], "slot_qubit": o[27:39]}
+    return g
+
+
+def _tswz(s):
+    return s ^ ((s >> 3) & 7)
+
+
+def _tma_ops(g, gbase):
+    """(smem slot base, [global index per box element in TMA linear order]) of every op of the tile at gbase:
+    coordinates exactly as the producer warp computes them, box traversal as the hardware does (dim 0 fastest)"""
+    ops = []
+    for e in range(1 << g["n_enum"]):
+        idx = gbase
+        for j, p in enumerate(g["enum_pos"]):
+            idx |= ((e >> j) & 1) << p
+        coord = [0] + [(idx >> g["dim_lo"][d]) & ((1 << g["dim_bits"][d]) - 1) for d in range(1, 5)]
+        elems = []
+        box = [1 << b for b in g["box_bits"]]
+        for b4 in range(box[4]):
+            for b3 in range(box[3]):
+                for b2 in range(box[2]):
+                    for b1 in range(box[1]):
+                        for b0 in range(box[0]):
+                            c = [coord[0] + b0, coord[1] + b1, coord[2] + b2, coord[3] + b3, coord[4] + b4]
+                            # element address = sum coordinate * stride (stride of dim d = 2^dim_lo[d] amplitudes)
+                            elems.append(sum(c[d] << g["dim_lo"][d] for d in range(5)))
+        ops.append((e << g["box_log2"], elems))
+    return ops
+
+
+def _mask(bits):
+    return sum(1 << b for b in bits)
+
+
+@pytest.mark.parametrize("n_local,tile_bits", [
+    (12, range(12)), (14, [0, 1, 2, 3, 6, 7, 8, 9, 10, 11, 12, 13]), (20, [0, 1, 2, 3, 5, 7, 9, 11, 13, 15, 17, 19]),
+    (30, [0, 1, 2, 3, 22, 23, 24, 25, 26, 27, 28, 29]), (30, [0, 1, 2, 5, 9, 12, 13, 14, 15, 16, 17, 18]),
+    (33, [0, 1, 2, 3, 10, 12, 14, 16, 18, 20, 30, 32]), (30, [0, 1, 2, 21, 22, 23, 24, 25, 26, 27, 28, 29]),
+    (24, [0, 1, 2, 3, 6, 7, 10, 11, 14, 15, 20, 21]),
+])
+def test_tma_tile_geometry_addresses_every_tile_amplitude_once(hl, n_local, tile_bits):
+    tile_mask = _mask(tile_bits)
+    """tma_tile_geometry: the TMA ops of a tile (coordinates as in the producer warp) touch exactly the tile's 2^12
+    amplitudes, each once, and shared-memory slot bit j holds index bit slot_qubit[j]."""
+    assert bin(tile_mask).count("1") == 12
+    g = _geometry(hl, tile_mask, n_local)
+    assert g is not None
+    # tensor-map constraints (cuTensorMapEncodeTiled): box <= 256, dims partition the index bits, strides < 2^40
+    assert g["dim_lo"][0] == 0 and g["dim_bits"][0] == 3 and g["box_bits"][0] == 3 and g["dim_lo"][1] == 3
+    for d in range(1, g["n_dims"]):
+        nxt = g["dim_lo"][d + 1] if d + 1 < g["n_dims"] else n_local
+        assert g["dim_lo"][d] + g["dim_bits"][d] == nxt and g["box_bits"][d] <= min(8, g["dim_bits"][d])
+        assert (16 << g["dim_lo"][d]) < (1 << 40)
+    assert g["box_log2"] >= 6 and g["box_log2"] + g["n_enum"] == 12
+    assert sorted(g["slot_qubit"]) == [q for q in range(64) if (tile_mask >> q) & 1]
+    rng = np.random.default_rng(1)
+    free = [q for q in range(n_local) if not (tile_mask >> q) & 1]
+    for _ in range(3):
+        t = int(rng.integers(0, 1 << len(free))) if free else 0
+        gbase = sum(((t >> j) & 1) << q for j, q in enumerate(free))
+        seen = {}
+        for slot_base, elems in _tma_ops(g, gbase):
+            for off, idx in enumerate(elems):
+                seen[slot_base + off] = idx
+        assert sorted(seen) == list(range(1 << 12))
+        for slot, idx in seen.items():
+            want = gbase | sum(((slot >> j) & 1) << g["slot_qubit"][j] for j in range(12))
+            assert idx == want, (slot, idx, want)
+
+
+@pytest.mark.parametrize("seed,n,tile_bits", [(1, 14, range(12)), (2, 14, [0, 1, 2, 3, 6, 7, 8, 9, 10, 11, 12, 13]),
+                                              (3, 15, [0, 1, 2, 3, 5, 6, 8, 9, 10, 12, 13, 14]), (4, 16, [0, 1, 2, 7, 8, 9, 10, 11, 12, 13, 14, 15])])
+def test_pipe_kernel_data_path_emulated(hl, seed, n, tile_bits):
+    tile_mask = _mask(tile_bits)
+    """k_tile_pipe emulated in numpy from exactly what launch_pass_pipe gives it: TMA ops into swizzled slots, rounds
+    (item -> slots through the descriptor bytes, variant selection, 8x8 mat-vec), TMA stores.  Equals the
+    gate-by-gate circuit; quarter-warp shared-memory accesses are conflict-free whenever the swizzle allows."""
+    assert bin(tile_mask).count("1") == 12
+    tq = [q for q in range(n) if (tile_mask >> q) & 1]
+    rng = np.random.default_rng(seed)
+    circ = []
+    samples = gates.all_gate_samples()
+    while len(circ) < 50:
+        g = samples[int(rng.integers(0, len(samples)))]
+        qs = [int(x) for x in rng.permutation(n)[:3]]
+        gg = g if rng.integers(0, 2) else gates.AppliedGate(g.matrix)
+        circ.append((gg, qs[0], qs[1] if g.nq > 1 else 0, qs[2] if g.nq > 2 else 0))
+    arr = pack(circ)
+    keep = []
+    for i in range(len(circ)):
+        op = HlOp()
+        hl.hl_classify(C.byref(arr, i * C.sizeof(_lib.GateStruct)), C.byref(op))
+        nd = [op.tgt[j] for j in range(op.n_tgt)] if op.kind != OP_DIAG else []
+        if all(q in tq for q in nd):
+            keep.append(i)
+    circ = [circ[i] for i in keep]
+    arr = pack(circ)
+    N = len(circ)
+    assert N > 15
+    geom = _geometry(hl, tile_mask, n)
+    assert geom is not None
+    R = N + 4
+    desc = (C.c_uint * (6 * R))()
+    max_mats = 8 * R
+    mats = (C.c_double * (128 * max_mats))()
+    hl.hl_pipe_pass.restype = C.c_int
+    nr = hl.hl_pipe_pass(arr, N, C.c_ulonglong(tile_mask), n, desc, mats, max_mats)
+    assert 0 < nr < N
+    M = np.frombuffer(mats, dtype=np.complex128).reshape(max_mats, 8, 8)
+    psi = random_state(n, 5)
+    want = psi.copy()
+    for g, q, c1, c2 in circ:
+        want = full_matrix_apply(want, g, [q, c1, c2], n)
+    got = psi.copy()
+    free = [q for q in range(n) if q not in tq]
+    tid = np.arange(512)
+    forced_conflicts = 0
+    for t in range(1 << len(free)):
+        gbase = sum(((t >> j) & 1) << q for j, q in enumerate(free))
+        ops = _tma_ops(geom, gbase)
+        smem = np.zeros(1 << 12, dtype=np.complex128)
+        for slot_base, elems in ops:                                     # UTMALDG with the 128 B swizzle
+            for off, idx in enumerate(elems):
+                smem[_tswz(slot_base + off)] = got[idx]
+        for r in range(nr):
+            rb, tb0, tb1, tb2, var, mat_off = [int(x) for x in desc[6 * r: 6 * r + 6]]
+            tb = [tb0, tb1, tb2]
+            so = [_tswz(1 << ((rb >> (8 * j)) & 31)) for j in range(3)]
+            lbase = np.zeros(512, dtype=np.int64)
+            for j in range(9):
+                lbase |= ((tid >> j) & 1) << ((tb[j >> 2] >> (8 * (j & 3))) & 31)
+            nvar = var & 0xFF
+            vidx = np.zeros(512, dtype=np.int64)
+            for j in range(nvar):
+                e = (var >> (8 + 8 * j)) & 0xFF
+                bit = ((gbase >> (e >> 1)) & 1) if (e & 1) else ((lbase >> (e >> 1)) & 1)
+                vidx |= bit << j
+            assert all(len(set(vidx[w * 32: w * 32 + 32])) == 1 for w in range(16)), "variant must be warp-uniform"
+            sl = _tswz(lbase)
+            sa = np.stack([sl ^ (so[0] if x & 1 else 0) ^ (so[1] if x & 2 else 0) ^ (so[2] if x & 4 else 0) for x in range(8)])
+            assert len(set(sa.ravel().tolist())) == 4096               # the round touches every slot exactly once
+            if t == 0:
+                # bank groups of a quarter-warp's 16 B accesses: conflict-free unless the round's register + variant
+                # bits cover BOTH slot bits of a swizzle class {c, c + 3}; then 2-way per class lost, never worse
+                deg = max(max(np.bincount(sa[x, qw * 8: qw * 8 + 8] & 7)) for x in range(8) for qw in range(64))
+                busy = {(rb >> (8 * j)) & 31 for j in range(3)}
+                for j in range(nvar):
+                    e = (var >> (8 + 8 * j)) & 0xFF
+                    if not e & 1:
+                        busy.add(e >> 1)
+                lost = sum(1 for c in range(3) if c in busy and c + 3 in busy)
+                assert deg == 1 << lost, (r, deg, lost, sorted(busy))
+                forced_conflicts += lost > 0
+            v = smem[sa]                                                # 8 x 512
+            out = np.einsum("gij,jg->ig", M[mat_off + vidx], v)
+            smem[sa] = out
+        for slot_base, elems in ops:                                     # UTMASTG
+            for off, idx in enumerate(elems):
+                got[idx] = smem[_tswz(slot_base + off)]
+    assert np.max(np.abs(got - want)) < 1e-13
+    assert forced_conflicts <= nr // 2
