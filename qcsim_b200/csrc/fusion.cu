@@ -69,7 +69,7 @@ static int launch_pass_pipe(qcsim_sv* h, const std::vector<Op>& all, const PassP
   int local_of[64];
   for (int q = 0; q < 64; ++q) local_of[q] = -1;
   for (int j = 0; j < k; ++j) local_of[plan.tile[j]] = j;
-  const std::vector<RoundPlan> rplan = schedule_rounds(all, plan, kMaxVariantBits, /*swizzle_kind=*/1);
+  const std::vector<RoundPlan> rplan = schedule_rounds(all, plan, kMaxVariantBits, /*swizzle_kind=*/2);
 
   static thread_local PipePassArgs A;  // ~30 KiB: keep it off the stack; the launch copies it
   {
@@ -244,8 +244,12 @@ int fusion_execute_local(qcsim_sv* h, const std::vector<Op>& ops) {
   static const int K_env = env_int("QCSIM_TILE_BITS", kMaxTileBits);
   static const int L_env = env_int("QCSIM_TILE_LOW", 4);
   static const int no_fuse = env_int("QCSIM_NO_FUSION", 0);
-  const int K = std::max(kRoundBits, std::min({K_env, kMaxTileBits, nl}));
-  const int L = std::max(1, std::min(L_env, K - kRoundBits));
+  static const int legacy = env_int("QCSIM_TILE_LEGACY", 0);
+  // TMA-staged pass (tile_pipe.cuh): 2^11-amplitude tiles whose innermost TMA box is qubits 0..2 (128 B);
+  // small registers and QCSIM_TILE_LEGACY=1 use the plain tile pass (2^12 tiles, 256 B runs)
+  const bool pipe = !legacy && nl >= kPipeTileBits && tensor_map_encoder() != nullptr;
+  const int K = pipe ? kPipeTileBits : std::max(kRoundBits, std::min({K_env, kMaxTileBits, nl}));
+  const int L = pipe ? 3 : std::max(1, std::min(L_env, K - kRoundBits));
   if (no_fuse || nl < 6 || N < 2) {
     for (const Op& op : ops) QCSIM_TRY(engine_launch_local(h, op));
     return QCSIM_OK;
@@ -283,9 +287,8 @@ int fusion_execute_local(qcsim_sv* h, const std::vector<Op>& ops) {
       for (int idx : st.pass.ops) QCSIM_TRY(engine_launch_local(h, ops[idx]));
       continue;
     }
-    static const int legacy = env_int("QCSIM_TILE_LEGACY", 0);
     int rc = QCSIM_ERR_UNSUPPORTED;
-    if (!legacy) rc = launch_pass_pipe(h, ops, st.pass);       // TMA-staged warp-specialised pass (tile_pipe.cuh)
+    if (pipe) rc = launch_pass_pipe(h, ops, st.pass);          // TMA-staged warp-specialised pass (tile_pipe.cuh)
     if (rc == QCSIM_ERR_UNSUPPORTED) rc = launch_pass(h, ops, st.pass, Lrun, rplan);  // small registers: plain tile pass
     QCSIM_TRY(rc);
   }

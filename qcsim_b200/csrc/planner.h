@@ -143,8 +143,9 @@ struct RoundPlan {
 };
 
 // swizzle_kind selects the shared-memory slot swizzle the low item bits must dodge: 0 = swz() of
-// common.cuh (every tile bit folds onto the low three, class = bit mod 3), 1 = the 128 B TMA swizzle of
-// tile_pipe.cuh (only slot bits 3..5 fold onto 0..2).
+// common.cuh (every tile bit folds onto the low three, class = bit mod 3), 1 = the 128 B TMA swizzle
+// (only slot bits 3..5 fold onto 0..2) with one item per lane, 2 = the TMA swizzle with the DMMA
+// fragment mapping of tile_pipe.cuh (register-bit order and item bits 0..2 chosen together).
 inline std::vector<RoundPlan> schedule_rounds(const std::vector<Op>& all, const PassPlan& plan, int max_variant_bits = 3,
                                               int swizzle_kind = 0) {
   const int k = (int)plan.tile.size();
@@ -248,13 +249,60 @@ inline std::vector<RoundPlan> schedule_rounds(const std::vector<Op>& all, const 
       while (order[pos] >= 0) ++pos;
       return pos;
     };
-    for (int res = 0; res < 3; ++res)
-      for (size_t i = 0; i < rest.size(); ++i)
-        if (rest[i] >= 0 && rest[i] % 3 == res && (swizzle_kind == 0 || rest[i] < 6)) {
-          order[next_free()] = rest[i];
-          rest[i] = -1;
-          break;
+    if (swizzle_kind == 2) {
+      // DMMA rounds on the TMA layout (tile_pipe.cuh).  Fragments move as 64-bit halves (LDS.64 / STS.64; odd
+      // k-lanes / odd rows take the imaginary half first), so a half-warp's 16 lanes must hit 16 distinct
+      // 8-byte columns of a 128 B row: column = 2 * bank(slot) + half.  The lanes of a half-warp differ in
+      //   fragment loads : item bits 0,1 (4 columns of the panel) x register bits 0,1 (the 4 k-lanes; bit 0 also picks the half)
+      //   result stores  : register bits 0,1 (4 rows; bit 0 also picks the half) x item bits 1,2
+      // Pick the order of the three register bits and the item bits (i0,i1,i2) with the fewest conflicts under tswz
+      // (only slot bits 0..5 move the bank: bank = (s ^ s >> 3) & 7).
+      auto bank = [](uint32_t s) { return (s ^ (s >> 3)) & 7u; };
+      auto degree = [&](uint32_t half_bit, uint32_t b1, uint32_t b2, uint32_t b3) {  // lanes: bit0 -> half_bit (+ half), bit1 -> b1, bit2 -> b2, bit3 -> b3
+        int cnt[16], worst = 0;
+        for (int c = 0; c < 16; ++c) cnt[c] = 0;
+        for (int lane = 0; lane < 16; ++lane) {
+          const uint32_t sidx = ((lane & 1) ? half_bit : 0u) ^ ((lane & 2) ? b1 : 0u) ^ ((lane & 4) ? b2 : 0u) ^ ((lane & 8) ? b3 : 0u);
+          worst = std::max(worst, ++cnt[2 * bank(sidx) + (lane & 1)]);
         }
+        return worst;
+      };
+      int best_cost = 1 << 30, best_r[3] = {rp.rbits[0], rp.rbits[1], rp.rbits[2]}, best_i[3] = {-1, -1, -1};
+      const int perms[6][3] = {{0, 1, 2}, {0, 2, 1}, {1, 0, 2}, {1, 2, 0}, {2, 0, 1}, {2, 1, 0}};
+      const int nrest = (int)rest.size();
+      for (const auto& pm : perms) {
+        const int r0 = rp.rbits[pm[0]], r1 = rp.rbits[pm[1]];
+        for (int a = 0; a < nrest; ++a)
+          for (int b = 0; b < nrest; ++b)
+            for (int c = 0; c < nrest; ++c) {
+              if (a == b || a == c || b == c) continue;
+              // loads: lane = 4 g + t: t bits -> (r0, r1), g bits 0,1 -> (i0, i1); stores: lane = 4 g + t: t bits -> (i1, i2), g bits 0,1 -> (r0, r1)
+              // (a half-warp of the store is lanes 0..15 = g 0..3: reorder so that bit0 is the half-selecting register bit)
+              const int cost = degree(1u << r0, 1u << r1, 1u << rest[a], 1u << rest[b]) + degree(1u << r0, 1u << r1, 1u << rest[b], 1u << rest[c]);
+              if (cost < best_cost) {
+                best_cost = cost;
+                for (int j = 0; j < 3; ++j) best_r[j] = rp.rbits[pm[j]];
+                best_i[0] = a;
+                best_i[1] = b;
+                best_i[2] = c;
+              }
+            }
+      }
+      for (int j = 0; j < 3; ++j) rp.rbits[j] = best_r[j];
+      if (best_i[0] >= 0)
+        for (int j = 0; j < 3; ++j) {
+          order[next_free()] = rest[best_i[j]];
+          rest[best_i[j]] = -1;
+        }
+    } else {
+      for (int res = 0; res < 3; ++res)
+        for (size_t i = 0; i < rest.size(); ++i)
+          if (rest[i] >= 0 && rest[i] % 3 == res && (swizzle_kind == 0 || rest[i] < 6)) {
+            order[next_free()] = rest[i];
+            rest[i] = -1;
+            break;
+          }
+    }
     for (int lb : rest)
       if (lb >= 0) order[next_free()] = lb;
     for (int j = 0; j < 9; ++j) rp.item_bit[j] = (j < ni && order[j] >= 0) ? order[j] : 0;

@@ -2,7 +2,8 @@
 // specialisation.  Same mathematics as tile_kernels.cuh (dense 8x8 rounds on a 2^12-amplitude
 // shared-memory tile), different machine mapping:
 //
-//   * one persistent CTA per SM: 8 consumer warps + 1 producer warp, THREE 64 KiB tile buffers;
+//   * one persistent CTA per SM: 2 consumer groups of 8 warps + 1 producer warp, SIX 32 KiB tile buffers
+//     (2^11 amplitudes: qubits 0..2 + 8 others); the groups take alternate tiles;
 //   * the producer warp moves tiles with cp.async.bulk.tensor (TMA, SASS UTMALDG / UTMASTG): the
 //     host describes the state vector as a rank-5 tensor whose dimensions are the contiguous groups
 //     of tile qubits (planner.h: tma_tile_geometry), so one TMA op brings a box of 2^(3+w) amplitudes
@@ -10,12 +11,21 @@
 //     transaction count (SYNCS), stores leave through bulk groups.  CU_TENSOR_MAP_SWIZZLE_128B makes
 //     the hardware XOR the 16 B chunk index with the 128 B row index: slot ^ ((slot >> 3) & 7), the
 //     bank swizzle the rounds need, for free;
-//   * while the consumers run the rounds of tile i, tile i+1 is landing, tile i-1 is draining and the
-//     load of tile i+2 is issued as soon as that drain has been read out: HBM traffic and the fp64
-//     pipe overlap instead of alternating (the round-1 kernel spent >50 % of its time in one or the
-//     other);
-//   * consumers synchronise among themselves with a named barrier (bar.sync 1, 256); the producer
-//     never joins it.
+//   * while the groups run the rounds of tiles i and i+1, tiles i+2, i+3 are landing, tiles i-1, i-2 are
+//     draining and the load of tile i+4 is issued as soon as the drain of its buffer has been read out:
+//     HBM traffic and the fp64 pipe overlap instead of alternating (the round-1 kernel spent >50 % of
+//     its time in one or the other);
+//   * a group synchronises its rounds with its own named barrier (bar.sync 1|2, 256); the producer never
+//     joins it, and the two groups drift apart, so one group's fragment loads / barrier waits are covered
+//     by the other group's MMAs;
+//   * a round is a 16x16 REAL matrix ([Re -Im; Im Re] of the 8x8 complex round matrix) times a
+//     16 x (items) panel: the consumers run it on the FP64 tensor path (mma.sync m8n8k4 f64, SASS
+//     DMMA.8x8x4), 8 instructions per 8 items.  tcgen05 has no f64 kind; DMMA is the Blackwell FP64
+//     matrix instruction and has the same 64 FMA/clk/SM peak as DFMA (tools/fp64_mix_bench.cu:
+//     63 vs 61 measured) -- the point is not more flops but operand delivery: the round matrix sits
+//     in 16 registers per lane for the whole round, where the DFMA mat-vec needed one 16-byte
+//     operand fetch per 4 DFMA and stalled the LSU / constant path at 46 % of the fp64 peak however
+//     the matrix was delivered (shared memory, indexed constants, uniform constant loads: measured).
 //
 // Reference loops replaced: QubitRegisterCalculator.h:39-939 (one OpenMP pass per gate).
 // Bound: HBM (32 B per amplitude per pass) up to ~3 dense rounds, fp64 pipe beyond.
@@ -28,11 +38,15 @@
 
 namespace qcsim {
 
-constexpr int kPipeStages = 3;
-constexpr int kPipeConsumerWarps = 8;
-constexpr int kPipeConsumers = kPipeConsumerWarps * 32;  // two round items (2 x 8 amplitudes) per thread: one matrix fetch feeds both
+constexpr int kPipeTileBits = 11;                        // 2^11 amplitudes = 32 KiB per tile
+constexpr int kPipeStages = 6;                           // tile buffers in the ring (192 KiB)
+constexpr int kPipeGroups = 2;                           // consumer groups; each works on its own tile
+constexpr int kPipeGroupWarps = 8;                       // a warp owns 32 round items = 4 MMA panels of 8 items
+constexpr int kPipeGroupThreads = kPipeGroupWarps * 32;
+constexpr int kPipeConsumerWarps = kPipeGroups * kPipeGroupWarps;
+constexpr int kPipeConsumers = kPipeConsumerWarps * 32;
 constexpr int kPipeThreads = kPipeConsumers + 32;        // + producer warp
-constexpr int kPipeTileBits = 12;
+constexpr int kPipeLookahead = 4;                        // tiles requested ahead of the one being drained
 constexpr uint32_t kPipeTileBytes = (uint32_t)sizeof(amp) << kPipeTileBits;
 
 struct PipePassArgs {
@@ -85,7 +99,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 // generic-proxy writes (st.shared by the consumers) -> visible to the async proxy (TMA store)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kPipeConsumers) : "memory"); }
+// named barrier of one consumer group (ids 1, 2); the producer and the other group never join it
+__device__ __forceinline__ void group_bar(uint32_t group) { asm volatile("bar.sync %0, %1;" ::"r"(group + 1u), "n"(kPipeGroupThreads) : "memory"); }
 
 __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
   asm volatile(
@@ -107,34 +122,14 @@ __device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_g
 }  // namespace pipe
 
 namespace pipe {
-// tile[sa*] = M_I * v* for two items, M_I = matrix slot I of the parameter block: the entries sit at compile-time
-// offsets of the parameter block, so they are fetched by uniform constant loads (LDCU.128 c[0x0][imm]) and reach
-// the DFMAs as uniform-register operands -- no shared-memory traffic; one fetch feeds 8 DFMAs (two items).
-template <int I>
-__device__ __forceinline__ void matvec8x2(const PipePassArgs& A, const amp (&v0)[8], const amp (&v1)[8], amp* __restrict__ tile,
-                                          const uint32_t (&sa)[8], uint32_t pair_off) {
-#pragma unroll
-  for (int row = 0; row < 8; row += 2) {  // two rows x two items = 8 independent DFMA chains
-    const amp ma = A.mats[I * kRoundMatAmps + row * 8], mb = A.mats[I * kRoundMatAmps + row * 8 + 8];
-    amp a0 = cmul(ma, v0[0]), a1 = cmul(ma, v1[0]);
-    amp b0 = cmul(mb, v0[0]), b1 = cmul(mb, v1[0]);
-#pragma unroll
-    for (int c = 1; c < 8; ++c) {
-      const amp xa = A.mats[I * kRoundMatAmps + row * 8 + c], xb = A.mats[I * kRoundMatAmps + row * 8 + 8 + c];
-      a0 = cfma(xa, v0[c], a0);
-      a1 = cfma(xa, v1[c], a1);
-      b0 = cfma(xb, v0[c], b0);
-      b1 = cfma(xb, v1[c], b1);
-    }
-    tile[sa[row]] = a0;  // only this thread touches these slots in this round, and it has read them all
-    tile[sa[row + 1]] = b0;
-    tile[sa[row] ^ pair_off] = a1;
-    tile[sa[row + 1] ^ pair_off] = b1;
-  }
+// D(8x8) += A(8x4) * B(4x8), fp64.  Fragments: A: lane holds A[lane >> 2][lane & 3]; B: lane holds
+// B[lane & 3][lane >> 2]; C/D: lane holds rows lane >> 2, columns 2 (lane & 3) and 2 (lane & 3) + 1.
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 }  // namespace pipe
 
-// Dynamic shared memory (1024 B aligned): 3 tile buffers | round matrices | mbarriers.
+// Dynamic shared memory (1024 B aligned): 6 tile buffers | round matrices | mbarriers.
 static __global__ void __launch_bounds__(kPipeThreads, 1) k_tile_pipe(const __grid_constant__ PipePassArgs A) {
   using namespace pipe;
   extern __shared__ __align__(16) unsigned char pipe_smem[];
@@ -156,6 +151,9 @@ static __global__ void __launch_bounds__(kPipeThreads, 1) k_tile_pipe(const __gr
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  // round matrices: parameter block -> shared memory once per CTA (a lane reads two entries per round; per-lane
+  // addresses would serialise in the constant cache)
+  for (uint32_t i = tid; i < (uint32_t)A.n_mats * kRoundMatAmps; i += kPipeThreads) smats[i] = A.mats[i];
   __syncthreads();
 
   auto gbase_of = [&](uint64_t t) {  // scatter the tile number into the non-tile index bits
@@ -199,20 +197,22 @@ static __global__ void __launch_bounds__(kPipeThreads, 1) k_tile_pipe(const __gr
       bulk_commit();  // every lane closes its own (possibly empty) group: group counts stay aligned across lanes
     };
     const uint64_t step = gridDim.x;
-    // prologue: two tiles in flight before the consumers start
-    if (blockIdx.x < A.n_tiles) issue_load(blockIdx.x, 0);
-    if (blockIdx.x + step < A.n_tiles) issue_load(blockIdx.x + step, 1);
+    // prologue: kPipeLookahead tiles in flight before the consumers start
+#pragma unroll 1
+    for (int j = 0; j < kPipeLookahead; ++j)
+      if (blockIdx.x + j * step < A.n_tiles) issue_load(blockIdx.x + j * step, j);
     uint32_t i = 0;
     for (uint64_t t = blockIdx.x; t < A.n_tiles; t += step, ++i) {
       const int s = (int)(i % kPipeStages);
       mbar_wait(&done[s], (i / kPipeStages) & 1u);  // rounds of tile i finished, fenced for the async proxy
       issue_store(t, s);
-      const uint64_t t2 = t + 2 * step;
+      const uint64_t t2 = t + kPipeLookahead * step;
       if (t2 < A.n_tiles) {
-        // the buffer of tile i+2 is the one tile i-1 is draining from: wait until that drain has read it
-        bulk_wait_read<1>();
+        // the buffer of tile i + lookahead is the one tile i + lookahead - stages drained from: wait until that
+        // drain has been read out of shared memory (all but the most recent stages - lookahead groups)
+        bulk_wait_read<kPipeStages - kPipeLookahead>();
         __syncwarp();
-        issue_load(t2, (int)((i + 2) % kPipeStages));
+        issue_load(t2, (int)((i + kPipeLookahead) % kPipeStages));
       }
     }
     bulk_wait<0>();  // all stores complete before the CTA exits
@@ -220,62 +220,135 @@ static __global__ void __launch_bounds__(kPipeThreads, 1) k_tile_pipe(const __gr
   }
 
   // ------------------------------------ consumer warps: the rounds ------------------------------------
-  uint32_t i = 0;
-  for (uint64_t t = blockIdx.x; t < A.n_tiles; t += gridDim.x, ++i) {
-    const int s = (int)(i % kPipeStages);
-    amp* const tile = tiles + (size_t)s * (1u << kPipeTileBits);
-    const uint64_t gbase = gbase_of(t);
-    mbar_wait(&full[s], (i / kPipeStages) & 1u);
+  // Round r multiplies every group of 8 amplitudes that differ in the round's 3 register bits by an 8x8 complex
+  // matrix M (one per value of the variant bits).  As a real product: [Re o; Im o] = [Re M, -Im M; Im M, Re M] [Re v; Im v].
+  // MMA mapping (per warp, 4 panels of 8 items): rows = output amplitude o (8) x part (2 M-blocks), columns = items,
+  // contraction = input amplitude a (8) x part = 4 K-blocks: kb = 2 part + (a >> 2), k = a & 3.
+  //   lane (g = lane >> 2, t = lane & 3) holds   A: M[g][t], M[g][4 + t] (16 registers, loaded once per round)
+  //                                              B: amplitudes t and 4 + t of item g of the panel (4 LDS.64)
+  //                                              D: output amplitude g of items 2t and 2t + 1 (4 STS.64)
+  // Fragments move as 64-bit halves: odd k-lanes (t & 1) fetch the imaginary half first, odd rows (g & 1) store it
+  // first, and the K-blocks / row blocks are permuted to match (a_first / a_second below).  A half-warp then covers
+  // 16 distinct 8-byte columns of a 128 B row even when register bit 0 sits where the TMA swizzle does not fold
+  // (planner.h, swizzle_kind 2).
+  // Item index (8 bits): bits 0..2 = column in the panel, bits 3..4 = panel, bits 5..7 = warp of the group.
+  // Two consumer groups take alternate tiles, each with its own named barrier: while one group waits for its
+  // fragment loads or its round barrier, the other keeps the fp64 pipe busy.
+  const uint32_t g = lane >> 2, tq = lane & 3u;
+  const uint32_t group = warp / kPipeGroupWarps, gwarp = warp % kPipeGroupWarps;
 
+  // Everything about a round that does not depend on the tile is computed ONCE per thread: the swizzled slots of
+  // its fragment loads / result stores, the slot strides of the panel / register / column bits, and the part of
+  // the variant index that comes from tile bits (warp-index bits).  The per-tile round body is then loads, 32
+  // DMMA, stores, barrier -- no dependent integer chain in front of the loads.
+  // (packed: slots are 11-bit numbers)  ls = load slot | store slot << 16, xa = x_hi | x_i0 << 16, xb = x_p0 | x_p1 << 16,
+  // ms = outside-tile variant selectors (3 bytes) | matrix base << 24
+  uint32_t ls[kMaxTileRounds], xa[kMaxTileRounds], xb[kMaxTileRounds], ms[kMaxTileRounds];
 #pragma unroll 1
-    for (int r = 0; r < A.n_rounds; ++r) {
+  for (int r = 0; r < kMaxTileRounds; ++r) {
+    ls[r] = xa[r] = xb[r] = ms[r] = 0;
+    if (r < A.n_rounds) {
       const TileRoundDesc rd = A.rounds[r];
-      const uint32_t so0 = tswz(1u << (rd.rb & 31u)), so1 = tswz(1u << ((rd.rb >> 8) & 31u)), so2 = tswz(1u << ((rd.rb >> 16) & 31u));
-      const int nvar = rd.var & 0xff;
-      // item index deposited on the non-round slot bits: a thread does items (tid, tid + 256); item bit 8 walks
-      // rd.tb byte 8 and never selects the matrix (the host keeps variant qubits on item bits 5..7)
-      uint32_t lbase = 0;
+      const uint32_t rb0 = 1u << (rd.rb & 31u), rb1 = 1u << ((rd.rb >> 8) & 31u), rb2 = 1u << ((rd.rb >> 16) & 31u);
+      auto ib = [&](int j) { return 1u << ((rd.tb[j >> 2] >> (8 * (j & 3))) & 31u); };  // slot bit walked by item bit j
+      uint32_t hi = 0;  // warp part of the item index (plain slot bits)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) lbase |= ((tid >> j) & 1u) << ((rd.tb[j >> 2] >> (8 * (j & 3))) & 31u);
-      const uint32_t pair_off = tswz(1u << (rd.tb[2] & 31u));
-      uint32_t vidx = 0;
+      for (int j = 0; j < 3; ++j) hi |= ((gwarp >> j) & 1u) ? ib(5 + j) : 0u;
+      const int nvar = rd.var & 0xff;
+      uint32_t vidx = 0, gs = 0;
 #pragma unroll
       for (int j = 0; j < kMaxVariantBits; ++j) {
         const uint32_t e = (rd.var >> (8 + 8 * j)) & 0xffu;
-        const uint32_t bit = (e & 1u) ? (uint32_t)((gbase >> (e >> 1)) & 1ULL) : ((lbase >> (e >> 1)) & 1u);
-        if (j < nvar) vidx |= bit << j;
+        if (j < nvar) {
+          if (e & 1u) gs |= (0x80u | (e >> 1)) << (8 * j);  // index bit outside the tile: resolved per tile
+          else vidx |= ((hi >> (e >> 1)) & 1u) << j;
+        }
       }
-      const uint32_t sl = tswz(lbase);
-      uint32_t sa[8];
-      amp v0[8], v1[8];
+      ms[r] = gs | ((rd.mat_off + vidx) << 24);
+      // slots: loads -- item g of the panel, amplitudes tq (+4); stores -- items 2 tq (+1), amplitude g
+      const uint32_t l0 = tswz(hi | ((g & 1u) ? ib(0) : 0u) | ((g & 2u) ? ib(1) : 0u) | ((g & 4u) ? ib(2) : 0u) | ((tq & 1u) ? rb0 : 0u) |
+                               ((tq & 2u) ? rb1 : 0u));
+      const uint32_t s0 = tswz(hi | ((tq & 1u) ? ib(1) : 0u) | ((tq & 2u) ? ib(2) : 0u) | ((g & 1u) ? rb0 : 0u) | ((g & 2u) ? rb1 : 0u) |
+                               ((g & 4u) ? rb2 : 0u));
+      ls[r] = l0 | (s0 << 16);
+      xa[r] = tswz(rb2) | (tswz(ib(0)) << 16);
+      xb[r] = tswz(ib(3)) | (tswz(ib(4)) << 16);
+    }
+  }
+
+  for (uint64_t t = blockIdx.x + (uint64_t)group * gridDim.x, i = group; t < A.n_tiles; t += (uint64_t)kPipeGroups * gridDim.x, i += kPipeGroups) {
+    const int s = (int)(i % kPipeStages);
+    amp* const tile = tiles + (size_t)s * (1u << kPipeTileBits);
+    const uint64_t gbase = gbase_of(t);
+    mbar_wait(&full[s], (uint32_t)(i / kPipeStages) & 1u);
+
+#pragma unroll 1
+    for (int r = 0; r < A.n_rounds; ++r) {
+      {
+        uint32_t midx = ms[r] >> 24;
+        const uint32_t ld0 = ls[r] & 0xffffu, st0 = ls[r] >> 16;
 #pragma unroll
-      for (int x = 0; x < 8; ++x) {
-        sa[x] = sl ^ ((x & 1) ? so0 : 0u) ^ ((x & 2) ? so1 : 0u) ^ ((x & 4) ? so2 : 0u);
-        v0[x] = tile[sa[x]];
-        v1[x] = tile[sa[x] ^ pair_off];
+        for (int j = 0; j < kMaxVariantBits; ++j) {
+          const uint32_t e = (ms[r] >> (8 * j)) & 0xffu;
+          if (e & 0x80u) midx += (uint32_t)((gbase >> (e & 0x7fu)) & 1ULL) << j;
+        }
+        // A fragments of this warp's matrix
+        const amp* __restrict__ M = smats + (size_t)midx * kRoundMatAmps;
+        const double2 m_lo = M[g * 8 + tq], m_hi = M[g * 8 + 4 + tq];
+        const uint32_t x_hi = xa[r] & 0xffffu, x_i0 = xa[r] >> 16, x_p0 = xb[r] & 0xffffu, x_p1 = xb[r] >> 16;
+        const double* const td = reinterpret_cast<const double*>(tile);
+        double* const tdw = reinterpret_cast<double*>(tile);
+        const uint32_t lq = tq & 1u, sq = g & 1u;  // half taken first by this lane's loads / stores (0 = real)
+        double b[4][4];                            // [panel][K-block]
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          const uint32_t a0 = ld0 ^ ((p & 1) ? x_p0 : 0u) ^ ((p & 2) ? x_p1 : 0u);
+          b[p][0] = td[2 * a0 + lq];
+          b[p][1] = td[2 * (a0 ^ x_hi) + lq];
+          b[p][2] = td[2 * a0 + (lq ^ 1u)];
+          b[p][3] = td[2 * (a0 ^ x_hi) + (lq ^ 1u)];
+        }
+        // contraction element of (K-block j, this lane): part = lq for j < 2, 1 - lq for j >= 2; amplitude tq + 4 (j & 1).
+        // Row blocks: the first accumulator holds the half this lane stores first (Re rows for even g, Im rows for odd g).
+        // Re row of o: [Re M | -Im M] over (Re v | Im v); Im row: [Im M | Re M].
+        const double re_row[4] = {lq ? -m_lo.y : m_lo.x, lq ? -m_hi.y : m_hi.x, lq ? m_lo.x : -m_lo.y, lq ? m_hi.x : -m_hi.y};
+        const double im_row[4] = {lq ? m_lo.x : m_lo.y, lq ? m_hi.x : m_hi.y, lq ? m_lo.y : m_lo.x, lq ? m_hi.y : m_hi.x};
+        double a_first[4], a_second[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          a_first[j] = sq ? im_row[j] : re_row[j];
+          a_second[j] = sq ? re_row[j] : im_row[j];
+        }
+        double c_first[4][2], c_second[4][2];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) c_first[p][0] = c_first[p][1] = c_second[p][0] = c_second[p][1] = 0.0;
+        // 8 independent accumulator chains (4 panels x 2 row blocks), 4 K-blocks deep
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) {
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            dmma884(c_first[p], a_first[kb], b[p][kb]);
+            dmma884(c_second[p], a_second[kb], b[p][kb]);
+          }
+        }
+        // mma.sync is warp-synchronous: every lane's loads of a panel are complete before any lane stores into it
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          const uint32_t a0 = st0 ^ ((p & 1) ? x_p0 : 0u) ^ ((p & 2) ? x_p1 : 0u);
+          tdw[2 * a0 + sq] = c_first[p][0];
+          tdw[2 * (a0 ^ x_i0) + sq] = c_first[p][1];
+          tdw[2 * a0 + (sq ^ 1u)] = c_second[p][0];
+          tdw[2 * (a0 ^ x_i0) + (sq ^ 1u)] = c_second[p][1];
+        }
+        if (r + 1 == A.n_rounds) fence_proxy_async();
+        group_bar(group);
       }
-      // The variant is warp-uniform by construction.  One straight-line body per matrix slot (see matvec8x2).
-      switch (rd.mat_off + vidx) {
-#define QCSIM_PIPE_CASE(I) \
-  case I:                  \
-    pipe::matvec8x2<I>(A, v0, v1, tile, sa, pair_off); \
-    break;
-        QCSIM_PIPE_CASE(0) QCSIM_PIPE_CASE(1) QCSIM_PIPE_CASE(2) QCSIM_PIPE_CASE(3) QCSIM_PIPE_CASE(4) QCSIM_PIPE_CASE(5) QCSIM_PIPE_CASE(6)
-        QCSIM_PIPE_CASE(7) QCSIM_PIPE_CASE(8) QCSIM_PIPE_CASE(9) QCSIM_PIPE_CASE(10) QCSIM_PIPE_CASE(11) QCSIM_PIPE_CASE(12) QCSIM_PIPE_CASE(13)
-        QCSIM_PIPE_CASE(14) QCSIM_PIPE_CASE(15) QCSIM_PIPE_CASE(16) QCSIM_PIPE_CASE(17) QCSIM_PIPE_CASE(18) QCSIM_PIPE_CASE(19) QCSIM_PIPE_CASE(20)
-        QCSIM_PIPE_CASE(21) QCSIM_PIPE_CASE(22) QCSIM_PIPE_CASE(23) QCSIM_PIPE_CASE(24) QCSIM_PIPE_CASE(25) QCSIM_PIPE_CASE(26) QCSIM_PIPE_CASE(27)
-#undef QCSIM_PIPE_CASE
-        default: break;
-      }
-      static_assert(kMaxTileMats == 28, "one switch case per matrix slot");
-      if (r + 1 == A.n_rounds) fence_proxy_async();
-      consumer_bar();
     }
     if (A.n_rounds == 0) {
       fence_proxy_async();
-      consumer_bar();
+      group_bar(group);
     }
-    if (tid == 0) mbar_arrive(&done[s]);
+    if (gwarp == 0 && lane == 0) mbar_arrive(&done[s]);
   }
 }
 

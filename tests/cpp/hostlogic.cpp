@@ -213,7 +213,7 @@ int hl_pipe_pass(const qcsim_gate* gates, int count, unsigned long long tile_mas
   int local_of[64];
   for (int q = 0; q < 64; ++q) local_of[q] = -1;
   for (int j = 0; j < g.k; ++j) local_of[plan.tile[j]] = j;
-  const std::vector<RoundPlan> rounds = schedule_rounds(ops, plan, 3, 1);
+  const std::vector<RoundPlan> rounds = schedule_rounds(ops, plan, 3, 2);
   int used = 0;
   for (size_t r = 0; r < rounds.size(); ++r) {
     const int nv = (int)rounds[r].vq.size();

@@ -322,6 +322,8 @@ def test_round_matrices_reproduce_the_circuit(hl, seed, tile):
 # ---- TMA-staged pass (tile_pipe.cuh): geometry + the kernel's index arithmetic, emulated -------------------
 def _geometry(hl, tile_mask, n_local):
     out = (C.c_int * 64)()
+    for i in range(64):
+        out[i] = 0
     hl.hl_tma_geometry.restype = C.c_int
     ok = hl.hl_tma_geometry(C.c_ulonglong(tile_mask), n_local, out)
     if not ok:
@@ -368,12 +370,15 @@ def _mask(bits):
     (30, [0, 1, 2, 3, 22, 23, 24, 25, 26, 27, 28, 29]), (30, [0, 1, 2, 5, 9, 12, 13, 14, 15, 16, 17, 18]),
     (33, [0, 1, 2, 3, 10, 12, 14, 16, 18, 20, 30, 32]), (30, [0, 1, 2, 21, 22, 23, 24, 25, 26, 27, 28, 29]),
     (24, [0, 1, 2, 3, 6, 7, 10, 11, 14, 15, 20, 21]),
+    (11, range(11)), (30, [0, 1, 2, 4, 7, 11, 12, 20, 25, 28, 29]), (33, [0, 1, 2, 24, 25, 26, 27, 28, 30, 31, 32]),
+    (30, [0, 1, 2, 3, 5, 7, 9, 11, 13, 15, 17]),
 ])
 def test_tma_tile_geometry_addresses_every_tile_amplitude_once(hl, n_local, tile_bits):
     tile_mask = _mask(tile_bits)
     """tma_tile_geometry: the TMA ops of a tile (coordinates as in the producer warp) touch exactly the tile's 2^12
     amplitudes, each once, and shared-memory slot bit j holds index bit slot_qubit[j]."""
-    assert bin(tile_mask).count("1") == 12
+    k = bin(tile_mask).count("1")
+    assert k in (11, 12)
     g = _geometry(hl, tile_mask, n_local)
     assert g is not None
     # tensor-map constraints (cuTensorMapEncodeTiled): box <= 256, dims partition the index bits, strides < 2^40
@@ -382,8 +387,8 @@ def test_tma_tile_geometry_addresses_every_tile_amplitude_once(hl, n_local, tile
         nxt = g["dim_lo"][d + 1] if d + 1 < g["n_dims"] else n_local
         assert g["dim_lo"][d] + g["dim_bits"][d] == nxt and g["box_bits"][d] <= min(8, g["dim_bits"][d])
         assert (16 << g["dim_lo"][d]) < (1 << 40)
-    assert g["box_log2"] >= 6 and g["box_log2"] + g["n_enum"] == 12
-    assert sorted(g["slot_qubit"]) == [q for q in range(64) if (tile_mask >> q) & 1]
+    assert g["box_log2"] >= 6 and g["box_log2"] + g["n_enum"] == k
+    assert sorted(g["slot_qubit"][:k]) == [q for q in range(64) if (tile_mask >> q) & 1]
     rng = np.random.default_rng(1)
     free = [q for q in range(n_local) if not (tile_mask >> q) & 1]
     for _ in range(3):
@@ -393,20 +398,21 @@ def test_tma_tile_geometry_addresses_every_tile_amplitude_once(hl, n_local, tile
         for slot_base, elems in _tma_ops(g, gbase):
             for off, idx in enumerate(elems):
                 seen[slot_base + off] = idx
-        assert sorted(seen) == list(range(1 << 12))
+        assert sorted(seen) == list(range(1 << k))
         for slot, idx in seen.items():
-            want = gbase | sum(((slot >> j) & 1) << g["slot_qubit"][j] for j in range(12))
+            want = gbase | sum(((slot >> j) & 1) << g["slot_qubit"][j] for j in range(k))
             assert idx == want, (slot, idx, want)
 
 
-@pytest.mark.parametrize("seed,n,tile_bits", [(1, 14, range(12)), (2, 14, [0, 1, 2, 3, 6, 7, 8, 9, 10, 11, 12, 13]),
-                                              (3, 15, [0, 1, 2, 3, 5, 6, 8, 9, 10, 12, 13, 14]), (4, 16, [0, 1, 2, 7, 8, 9, 10, 11, 12, 13, 14, 15])])
+@pytest.mark.parametrize("seed,n,tile_bits", [(1, 13, range(11)), (2, 14, [0, 1, 2, 3, 6, 7, 8, 9, 10, 12, 13]),
+                                              (3, 15, [0, 1, 2, 3, 5, 6, 8, 9, 12, 13, 14]), (4, 16, [0, 1, 2, 8, 9, 10, 11, 12, 13, 14, 15])])
 def test_pipe_kernel_data_path_emulated(hl, seed, n, tile_bits):
     tile_mask = _mask(tile_bits)
-    """k_tile_pipe emulated in numpy from exactly what launch_pass_pipe gives it: TMA ops into swizzled slots, rounds
-    (item -> slots through the descriptor bytes, variant selection, 8x8 mat-vec), TMA stores.  Equals the
-    gate-by-gate circuit; quarter-warp shared-memory accesses are conflict-free whenever the swizzle allows."""
-    assert bin(tile_mask).count("1") == 12
+    """k_tile_pipe emulated in numpy from exactly what launch_pass_pipe gives it: TMA ops into swizzled slots, rounds in
+    the kernel's MMA mapping (lane (g, t): B fragment = amplitudes t, 4 + t of item g; D fragment = output amplitude g of
+    items 2t, 2t + 1; warp-uniform variant selection), TMA stores.  Equals the gate-by-gate circuit."""
+    K = 11                                                                # kPipeTileBits
+    assert bin(tile_mask).count("1") == K
     tq = [q for q in range(n) if (tile_mask >> q) & 1]
     rng = np.random.default_rng(seed)
     circ = []
@@ -444,49 +450,76 @@ def test_pipe_kernel_data_path_emulated(hl, seed, n, tile_bits):
         want = full_matrix_apply(want, g, [q, c1, c2], n)
     got = psi.copy()
     free = [q for q in range(n) if q not in tq]
-    tid = np.arange(512)
-    forced_conflicts = 0
+    lane = np.arange(32)
+    g, tq4 = lane >> 2, lane & 3
+    degrees = []
     for t in range(1 << len(free)):
         gbase = sum(((t >> j) & 1) << q for j, q in enumerate(free))
         ops = _tma_ops(geom, gbase)
-        smem = np.zeros(1 << 12, dtype=np.complex128)
+        smem = np.zeros(1 << K, dtype=np.complex128)
         for slot_base, elems in ops:                                     # UTMALDG with the 128 B swizzle
             for off, idx in enumerate(elems):
                 smem[_tswz(slot_base + off)] = got[idx]
         for r in range(nr):
             rb, tb0, tb1, tb2, var, mat_off = [int(x) for x in desc[6 * r: 6 * r + 6]]
             tb = [tb0, tb1, tb2]
-            so = [_tswz(1 << ((rb >> (8 * j)) & 31)) for j in range(3)]
-            lbase = np.zeros(512, dtype=np.int64)
-            for j in range(9):
-                lbase |= ((tid >> j) & 1) << ((tb[j >> 2] >> (8 * (j & 3))) & 31)
+            rbit = [1 << ((rb >> (8 * j)) & 31) for j in range(3)]
+            ib = [1 << ((tb[j >> 2] >> (8 * (j & 3))) & 31) for j in range(K - 3)]
+            assert sorted(rbit + ib) == [1 << j for j in range(K)]       # register + item bits = all slot bits
             nvar = var & 0xFF
-            vidx = np.zeros(512, dtype=np.int64)
-            for j in range(nvar):
-                e = (var >> (8 + 8 * j)) & 0xFF
-                bit = ((gbase >> (e >> 1)) & 1) if (e & 1) else ((lbase >> (e >> 1)) & 1)
-                vidx |= bit << j
-            assert all(len(set(vidx[w * 32: w * 32 + 32])) == 1 for w in range(16)), "variant must be warp-uniform"
-            sl = _tswz(lbase)
-            sa = np.stack([sl ^ (so[0] if x & 1 else 0) ^ (so[1] if x & 2 else 0) ^ (so[2] if x & 4 else 0) for x in range(8)])
-            assert len(set(sa.ravel().tolist())) == 4096               # the round touches every slot exactly once
-            if t == 0:
-                # bank groups of a quarter-warp's 16 B accesses: conflict-free unless the round's register + variant
-                # bits cover BOTH slot bits of a swizzle class {c, c + 3}; then 2-way per class lost, never worse
-                deg = max(max(np.bincount(sa[x, qw * 8: qw * 8 + 8] & 7)) for x in range(8) for qw in range(64))
-                busy = {(rb >> (8 * j)) & 31 for j in range(3)}
+            touched_d = np.zeros(2 << K, dtype=int)
+            new_smem = smem.copy()
+            for warp in range(8):                                        # the 8 warps of one consumer group
+                hi = sum(ib[5 + j] for j in range(3) if (warp >> j) & 1)
+                vidx = 0
                 for j in range(nvar):
                     e = (var >> (8 + 8 * j)) & 0xFF
-                    if not e & 1:
-                        busy.add(e >> 1)
-                lost = sum(1 for c in range(3) if c in busy and c + 3 in busy)
-                assert deg == 1 << lost, (r, deg, lost, sorted(busy))
-                forced_conflicts += lost > 0
-            v = smem[sa]                                                # 8 x 512
-            out = np.einsum("gij,jg->ig", M[mat_off + vidx], v)
-            smem[sa] = out
+                    bit = ((gbase >> (e >> 1)) & 1) if (e & 1) else ((hi >> (e >> 1)) & 1)
+                    vidx |= bit << j
+                Mv = M[mat_off + vidx]
+                ld0 = _tswz(hi | np.where(g & 1, ib[0], 0) | np.where(g & 2, ib[1], 0) | np.where(g & 4, ib[2], 0)
+                            | np.where(tq4 & 1, rbit[0], 0) | np.where(tq4 & 2, rbit[1], 0))
+                st0 = _tswz(hi | np.where(tq4 & 1, ib[1], 0) | np.where(tq4 & 2, ib[2], 0) | np.where(g & 1, rbit[0], 0)
+                            | np.where(g & 2, rbit[1], 0) | np.where(g & 4, rbit[2], 0))
+                x_hi, x_i0, x_p0, x_p1 = _tswz(rbit[2]), _tswz(ib[0]), _tswz(ib[3]), _tswz(ib[4])
+                lq, sq = tq4 & 1, g & 1                                  # half fetched / stored first by the lane
+                td = smem.view(np.float64)                               # td[2 * slot + part]
+                tdw = new_smem.view(np.float64)
+                for p in range(4):
+                    a0 = ld0 ^ (x_p0 if p & 1 else 0) ^ (x_p1 if p & 2 else 0)
+                    loads = [2 * a0 + lq, 2 * (a0 ^ x_hi) + lq, 2 * a0 + (lq ^ 1), 2 * (a0 ^ x_hi) + (lq ^ 1)]   # 4 LDS.64, K-block j
+                    for addr in loads:
+                        touched_d[addr] += 1
+                    bfr = [td[addr] for addr in loads]
+                    # real 16 x 16 product through the fragments: contraction element of (K-block j, lane) is
+                    # (part = lq for j < 2 else 1 - lq, amplitude tq + 4 (j & 1)) of item g
+                    vre = np.zeros((8, 8))
+                    vim = np.zeros((8, 8))
+                    for j in range(4):
+                        part = np.where(j < 2, lq, lq ^ 1)
+                        amp_i = tq4 + 4 * (j & 1)
+                        vre[g[part == 0], amp_i[part == 0]] = bfr[j][part == 0]
+                        vim[g[part == 1], amp_i[part == 1]] = bfr[j][part == 1]
+                    out = (vre + 1j * vim) @ Mv.T                        # out[n][o] = sum_a M[o][a] v[n][a]
+                    s0 = st0 ^ (x_p0 if p & 1 else 0) ^ (x_p1 if p & 2 else 0)
+                    o0, o1 = out[2 * tq4, g], out[2 * tq4 + 1, g]        # D fragments: row o = g, columns 2 tq, 2 tq + 1
+                    first0 = np.where(sq == 1, o0.imag, o0.real)
+                    first1 = np.where(sq == 1, o1.imag, o1.real)
+                    second0 = np.where(sq == 1, o0.real, o0.imag)
+                    second1 = np.where(sq == 1, o1.real, o1.imag)
+                    stores = [(2 * s0 + sq, first0), (2 * (s0 ^ x_i0) + sq, first1), (2 * s0 + (sq ^ 1), second0), (2 * (s0 ^ x_i0) + (sq ^ 1), second1)]
+                    for addr, val in stores:
+                        tdw[addr] = val
+                    assert sorted(np.concatenate([a for a, _ in stores]).tolist()) == sorted(np.concatenate(loads).tolist())
+                    if t == 0:                                           # half-warp 8-byte columns of the LDS.64 / STS.64
+                        for addr in loads + [a for a, _ in stores]:
+                            degrees.append(max(max(np.bincount(addr[q * 16: q * 16 + 16] & 15, minlength=16)) for q in range(2)))
+            assert np.all(touched_d == 1)                                # the round reads every 8-byte half exactly once
+            smem = new_smem
         for slot_base, elems in ops:                                     # UTMASTG
             for off, idx in enumerate(elems):
                 got[idx] = smem[_tswz(slot_base + off)]
     assert np.max(np.abs(got - want)) < 1e-13
-    assert forced_conflicts <= nr // 2
+    # bank conflicts of the fragment accesses: the planner picks the register-bit order and item bits 0..2 to dodge them;
+    # what remains is forced by register bits that sit above slot bit 5 (the TMA swizzle does not fold those)
+    assert max(degrees) <= 2 and np.mean(degrees) < 1.5, (max(degrees), np.mean(degrees))
