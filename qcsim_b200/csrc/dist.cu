@@ -256,41 +256,66 @@ static int allgather_host(qcsim_sv* h, const double* mine, int per, double* all)
 }
 
 // ---- peer-memory exchange kernel --------------------------------------------------------------------
-// In-place swap of my block with the matching block of each peer, straight over NVLink: no staging
-// buffer, no second copy.  Of every pair of ranks, the lower one swaps the first half of the block
-// and the higher one the second half, so each direction of each link carries the same load
-// (half as remote stores issued here, half as remote loads issued by the peer).
+// In-place swap of physical index bits gpos[j] (rank bits) with local bits lpos[j], straight over NVLink: no
+// staging buffer, no second copy.  For rank r with value a on the swapped global bits and every t != a, the
+// amplitudes of r whose local bits lpos hold t trade places with the amplitudes of peer(t) whose local bits lpos
+// hold a.  Of every pair of ranks the lower one swaps the first half of the (strided) block and the higher one
+// the second half, so each direction of each link carries the same load (half as remote stores issued here,
+// half as remote loads issued by the peer).  The partner bits may sit anywhere in the local index: the block is a
+// set of runs of 2^(lowest partner position) amplitudes, addressed like a controlled gate addresses its subspace.
 struct SwapArgs {
   int n_peers;
-  amp* remote[7];        // peer's slice + offset of the block it trades with me
-  uint64_t mine_off[7];  // offset of my block for that peer
-  uint64_t first[7];     // my share of the block: [first, first + count)
-  uint64_t count[7];     // in units of amp2 (two amplitudes, 32 bytes)
+  FixedBits fix;           // the local partner positions, ascending (removed from the work-item index)
+  amp* remote[7];          // peer's slice
+  uint64_t mine_or[7];     // partner bits set to t (my side of the trade with that peer)
+  uint64_t remote_or[7];   // partner bits set to a (the peer's side)
+  uint64_t first[7];       // my share of the block: work items [first, first + count)
+  uint64_t count[7];       // in units of amp2 (two adjacent amplitudes, 32 bytes) -- or single amplitudes (k_exchange_swap_v1)
 };
 
 __global__ void __launch_bounds__(256) k_exchange_swap(amp* __restrict__ mine, const __grid_constant__ SwapArgs A) {
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (int p = 0; p < A.n_peers; ++p) {
-    amp* m = mine + A.mine_off[p] + 2 * A.first[p];
-    amp* r = A.remote[p] + 2 * A.first[p];
-    const uint64_t n2 = A.count[p];
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (; i + 3 * stride < n2; i += 4 * stride) {  // 4 x 32 B remote loads in flight per thread
+    amp* const m = mine + A.mine_or[p];
+    amp* const r = A.remote[p] + A.remote_or[p];
+    const uint64_t lo = A.first[p], hi = A.first[p] + A.count[p];
+    uint64_t i = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < hi; i += 4 * stride) {  // 4 x 32 B remote loads in flight per thread
       amp2 x[4], y[4];
+      uint64_t o[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) y[u] = ld_amp2(r + 2 * (i + u * stride));
+      for (int u = 0; u < 4; ++u) o[u] = scatter_index(2 * (i + u * stride), A.fix);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) x[u] = ld_amp2(m + 2 * (i + u * stride));
+      for (int u = 0; u < 4; ++u) y[u] = ld_amp2(r + o[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) x[u] = ld_amp2(m + o[u]);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        st_amp2(m + 2 * (i + u * stride), y[u]);
-        st_amp2(r + 2 * (i + u * stride), x[u]);
+        st_amp2(m + o[u], y[u]);
+        st_amp2(r + o[u], x[u]);
       }
     }
-    for (; i < n2; i += stride) {
-      const amp2 y = ld_amp2(r + 2 * i), x = ld_amp2(m + 2 * i);
-      st_amp2(m + 2 * i, y);
-      st_amp2(r + 2 * i, x);
+    for (; i < hi; i += stride) {
+      const uint64_t o = scatter_index(2 * i, A.fix);
+      const amp2 y = ld_amp2(r + o), x = ld_amp2(m + o);
+      st_amp2(m + o, y);
+      st_amp2(r + o, x);
+    }
+  }
+}
+
+// a partner on local bit 0: single amplitudes (tiny registers only; the planner avoids low partner positions)
+__global__ void __launch_bounds__(256) k_exchange_swap_v1(amp* __restrict__ mine, const __grid_constant__ SwapArgs A) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (int p = 0; p < A.n_peers; ++p) {
+    amp* const m = mine + A.mine_or[p];
+    amp* const r = A.remote[p] + A.remote_or[p];
+    const uint64_t hi = A.first[p] + A.count[p];
+    for (uint64_t i = A.first[p] + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += stride) {
+      const uint64_t o = scatter_index(i, A.fix);
+      const amp y = r[o], x = m[o];
+      m[o] = y;
+      r[o] = x;
     }
   }
 }
@@ -396,14 +421,42 @@ static void harvest_timings(qcsim_sv* h, bool wait) {
   cudaGetLastError();  // cudaEventQuery's cudaErrorNotReady is not an error
 }
 
+static int do_exchange_nccl_top(qcsim_sv* h, const DistStep& ex);
+
 static int do_exchange(qcsim_sv* h, const DistStep& ex) {
   DistState* d = st(h);
   const int k = ex.k, nl = h->n_local;
-  if (k < 1 || k > 3) return fail(QCSIM_ERR_BAD_ARG, "internal: bad exchange width");
-  QCSIM_TRY(spmd_note(h, 3, (uint64_t)k, (uint64_t)ex.gpos[0] | ((uint64_t)ex.gpos[1] << 8) | ((uint64_t)ex.gpos[2] << 16)));
+  if (k < 1 || k > kMaxExchange) return fail(QCSIM_ERR_BAD_ARG, "internal: bad exchange width");
+  for (int j = 0; j < k; ++j)
+    if (ex.gpos[j] < nl || ex.gpos[j] >= h->n || ex.lpos[j] < 0 || ex.lpos[j] >= nl) return fail(QCSIM_ERR_BAD_ARG, "internal: bad exchange positions");
+  QCSIM_TRY(spmd_note(h, 3, (uint64_t)k,
+                      (uint64_t)ex.gpos[0] | ((uint64_t)ex.gpos[1] << 8) | ((uint64_t)ex.gpos[2] << 16) | ((uint64_t)ex.lpos[0] << 24) |
+                          ((uint64_t)ex.lpos[1] << 32) | ((uint64_t)ex.lpos[2] << 40)));
   harvest_timings(h, false);
-  const uint64_t blk = h->dim_local >> k;  // amps per sub-block
-  const uint64_t chunk = std::min<uint64_t>(blk, stage_chunk_amps());
+  if (!d->p2p) {
+    // NCCL send/recv moves contiguous blocks: park the partners on the top k local positions (one local
+    // permutation pass), exchange there, and put them back
+    bool top = true;
+    for (int j = 0; j < k; ++j) top = top && ex.lpos[j] == nl - k + j;
+    if (top) return do_exchange_nccl_top(h, ex);
+    int src_of[64];
+    for (int p = 0; p < 64; ++p) src_of[p] = p;
+    for (int j = 0; j < k; ++j) {  // bring what sat on lpos[j] to the top slot nl-k+j (a product of position swaps)
+      int pa = -1;
+      for (int p = 0; p < nl; ++p)
+        if (src_of[p] == ex.lpos[j]) pa = p;
+      std::swap(src_of[pa], src_of[nl - k + j]);
+    }
+    int inv[64];
+    for (int p = 0; p < 64; ++p) inv[p] = p;
+    for (int p = 0; p < nl; ++p) inv[src_of[p]] = p;
+    DistStep t = ex;
+    for (int j = 0; j < k; ++j) t.lpos[j] = nl - k + j;
+    QCSIM_TRY(engine_permute_bits(h, src_of));
+    QCSIM_TRY(do_exchange_nccl_top(h, t));
+    return engine_permute_bits(h, inv);
+  }
+  const uint64_t blk = h->dim_local >> k;  // amplitudes per sub-block
   const int n_sub = 1 << k;
   int a = 0;  // my value of the swapped global bits
   for (int j = 0; j < k; ++j) a |= ((h->rank >> (ex.gpos[j] - nl)) & 1) << j;
@@ -415,43 +468,77 @@ static int do_exchange(qcsim_sv* h, const DistStep& ex) {
     }
     return p;
   };
-  auto slot = [&](int buf, int t) { return d->stage + ((uint64_t)(buf * (n_sub - 1) + (t < a ? t : t - 1))) * d->stage_chunk; };
-
+  auto deposit = [&](int v) {  // value v of the k swapped bits -> local partner bits
+    uint64_t o = 0;
+    for (int j = 0; j < k; ++j)
+      if ((v >> j) & 1) o |= 1ULL << ex.lpos[j];
+    return o;
+  };
   cudaEvent_t e0, e1;
   CUDA_TRY(cudaEventCreate(&e0));
   CUDA_TRY(cudaEventCreate(&e1));
-  if (d->p2p) {
-    SwapArgs A;
-    std::memset(&A, 0, sizeof A);
-    // peers in XOR order: in step d every rank of the group talks to rank ^ d -- a perfect
-    // matching, so no rank is the target of everybody at once
-    for (int dd = 1; dd < n_sub; ++dd) {
-      const int t = a ^ dd;
-      const int peer = peer_of(t);
-      const int j = A.n_peers++;
-      A.remote[j] = d->peer_psi[peer] + (uint64_t)a * blk;  // the peer trades its block `a` for my block `t`
-      A.mine_off[j] = (uint64_t)t * blk;
-      const uint64_t pairs = blk / 2;  // amp2 units; blk is a power of two >= 2 here
-      if (pairs < 2) {
-        A.first[j] = 0;
-        A.count[j] = h->rank < peer ? pairs : 0;
-      } else {
-        A.first[j] = h->rank < peer ? 0 : pairs / 2;
-        A.count[j] = pairs / 2;
-      }
+  SwapArgs A;
+  std::memset(&A, 0, sizeof A);
+  int sorted[kMaxExchange];
+  for (int j = 0; j < k; ++j) sorted[j] = ex.lpos[j];
+  std::sort(sorted, sorted + k);
+  A.fix.n = k;
+  for (int j = 0; j < 3; ++j) A.fix.pos[j] = j < k ? sorted[j] : 0;
+  const bool wide = sorted[0] >= 1 && blk >= 4;  // 32-byte units
+  const uint64_t units = wide ? blk / 2 : blk;
+  // peers in XOR order: in step d every rank of the group talks to rank ^ d -- a perfect matching, so no rank is
+  // the target of everybody at once
+  for (int dd = 1; dd < n_sub; ++dd) {
+    const int t = a ^ dd;
+    const int peer = peer_of(t);
+    const int j = A.n_peers++;
+    A.remote[j] = d->peer_psi[peer];
+    A.mine_or[j] = deposit(t);    // my amplitudes with partner bits = t ...
+    A.remote_or[j] = deposit(a);  // ... trade with the peer's amplitudes with partner bits = a
+    if (units < 2) {
+      A.first[j] = 0;
+      A.count[j] = h->rank < peer ? units : 0;
+    } else {
+      A.first[j] = h->rank < peer ? 0 : units / 2;
+      A.count[j] = units / 2;
     }
-    QCSIM_TRY(stream_barrier(h));  // every rank has finished writing its slice
-    CUDA_TRY(cudaEventRecord(e0, h->stream));
-    k_exchange_swap<<<kNumSMs * 8, 256, 0, h->stream>>>(h->psi, A);
-    CUDA_TRY(cudaGetLastError());
-    QCSIM_TRY(stream_barrier(h));  // every rank has finished swapping
-    CUDA_TRY(cudaEventRecord(e1, h->stream));
-    d->timed.push_back({e0, e1});
-    h->stats.kernel_launches += 1;
-    h->stats.exchange_calls += 1;
-    h->stats.exchange_bytes += (uint64_t)(n_sub - 1) * blk * sizeof(amp);
-    return QCSIM_OK;
   }
+  QCSIM_TRY(stream_barrier(h));  // every rank has finished writing its slice
+  CUDA_TRY(cudaEventRecord(e0, h->stream));
+  if (wide) k_exchange_swap<<<kNumSMs * 8, 256, 0, h->stream>>>(h->psi, A);
+  else k_exchange_swap_v1<<<kNumSMs * 8, 256, 0, h->stream>>>(h->psi, A);
+  CUDA_TRY(cudaGetLastError());
+  QCSIM_TRY(stream_barrier(h));  // every rank has finished swapping
+  CUDA_TRY(cudaEventRecord(e1, h->stream));
+  d->timed.push_back({e0, e1});
+  h->stats.kernel_launches += 1;
+  h->stats.exchange_calls += 1;
+  h->stats.exchange_bytes += (uint64_t)(n_sub - 1) * blk * sizeof(amp);
+  return QCSIM_OK;
+}
+
+// NCCL send/recv path (QCSIM_EXCHANGE=nccl or no peer access): the partners are the top k local positions, so every
+// peer's share is one contiguous block; double-buffered staging
+static int do_exchange_nccl_top(qcsim_sv* h, const DistStep& ex) {
+  DistState* d = st(h);
+  const int k = ex.k, nl = h->n_local;
+  const uint64_t blk = h->dim_local >> k;
+  const uint64_t chunk = std::min<uint64_t>(blk, stage_chunk_amps());
+  const int n_sub = 1 << k;
+  int a = 0;
+  for (int j = 0; j < k; ++j) a |= ((h->rank >> (ex.gpos[j] - nl)) & 1) << j;
+  auto peer_of = [&](int t) {
+    int p = h->rank;
+    for (int j = 0; j < k; ++j) {
+      const int bit = 1 << (ex.gpos[j] - nl);
+      p = ((t >> j) & 1) ? (p | bit) : (p & ~bit);
+    }
+    return p;
+  };
+  auto slot = [&](int buf, int t) { return d->stage + ((uint64_t)(buf * (n_sub - 1) + (t < a ? t : t - 1))) * d->stage_chunk; };
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
   QCSIM_TRY(ensure_stage(h, chunk, n_sub - 1));
   CUDA_TRY(cudaEventRecord(e0, h->stream));
   const uint64_t n_chunks = (blk + chunk - 1) / chunk;
@@ -512,48 +599,69 @@ int dist_canonicalize(qcsim_sv* h) {
   return run_steps(h, dist_plan_canonicalize(d->layout));
 }
 
-// QFT / IQFT on a sharded register (see engine_qft).  The transform's local part runs as radix-8
-// passes on every shard; the qubits that live on global positions are brought down with ONE
-// exchange, transformed in one pass whose twiddles read the rank bits, and sent back -- two
-// all-to-all phases in total.  The qubit reversal stays a relabelling.
+// QFT / IQFT on a sharded register (see engine_qft), in WHATEVER layout the register is in: the qubit reversal
+// (QubitsSwapper, QubitsSwapper.h:23-34) is a relabelling, and nothing is canonicalised between chained
+// transforms.  The targets are processed in the reference's order (QuantumFourierTransform.h:35-87: top-down
+// for the QFT, bottom-up for the IQFT) as runs of qubits that sit on local positions -- radix-8 passes whose
+// twiddles gather the lower qubits bit by bit, rank bits included.  When the next target sits on a global
+// position, ONE exchange brings every unprocessed global target down, trading against (in this order) local
+// qubits outside the transform, targets that are already done, targets that come last; partners may be any local
+// position (k_exchange_swap), so there is no parking pass.
 int dist_qft(qcsim_sv* h, int sq, int eq, bool do_swap, bool inverse, int* handled) {
   DistState* d = st(h);
   DistLayout& Lo = d->layout;
-  const int nl = h->n_local;
-  *handled = 0;
-  if (sq >= nl) return QCSIM_OK;  // transform entirely on global qubits: gate-by-gate path
+  const int nl = h->n_local, n = h->n;
+  *handled = 1;
   auto virtual_swaps = [&]() {
     for (int s = sq, e = eq; s < e; ++s, --e) Lo.swap_logical(s, e);
   };
   if (inverse && do_swap) virtual_swaps();  // QubitsSwapper first (QuantumFourierTransform.h:67)
-  QCSIM_TRY(dist_canonicalize(h));          // the passes below assume logical == physical
-  const QftSegment ident = {0, h->n, 0, 0};
-  const int gg = eq >= nl ? eq - nl + 1 : 0;  // transform qubits on global positions
-  const int leq = std::min(eq, nl - 1);
-  DistStep ex;
-  ex.exchange = true;
-  ex.k = gg;
-  for (int j = 0; j < gg; ++j) {
-    ex.gpos[j] = nl + j;
-    ex.lpos[j] = nl - gg + j;
-  }
-  QftSegment seg[2] = {{0, nl - gg, 0, 0}, {nl, gg, nl - gg, 0}};
-  auto top_pass = [&]() -> int {
-    // global positions nl..eq <-> local positions nl-gg..nl-1, transform there, and back
+  const int step = inverse ? 1 : -1;
+  int cur = inverse ? sq : eq;
+  auto pending = [&](int q) { return inverse ? (q >= cur && q <= eq) : (q <= cur && q >= sq); };
+  while (inverse ? cur <= eq : cur >= sq) {
+    if (!Lo.is_global(cur)) {
+      int end = cur;  // maximal run of local targets in processing order
+      while ((inverse ? end + 1 <= eq : end - 1 >= sq) && !Lo.is_global(end + step)) end += step;
+      QCSIM_TRY(engine_qft_passes(h, std::min(cur, end), std::max(cur, end), inverse, sq, Lo.phys_of));
+      cur = end + step;
+      continue;
+    }
+    // bring every pending global target down with one exchange
+    std::vector<int> in_q;
+    for (int q = cur; pending(q) && (int)in_q.size() < kMaxExchange; q += step)
+      if (Lo.is_global(q)) in_q.push_back(q);
+    struct Cand { int cls, order, pos, q; };
+    std::vector<Cand> cand;
+    const int min_pos = std::min(kMinExchangePos, std::max(0, nl - (n - nl) - 1));
+    for (int q = 0; q < n; ++q) {
+      if (Lo.is_global(q)) continue;
+      Cand c;
+      c.q = q;
+      c.pos = Lo.phys_of[q];
+      if (q < sq || q > eq) c.cls = 0, c.order = 0;                     // not part of the transform
+      else if (!pending(q)) c.cls = 1, c.order = 0;                     // already transformed
+      else c.cls = 2, c.order = inverse ? (eq - q) : (q - sq);          // pending: the one processed last goes first
+      if (c.pos < min_pos) c.cls += 3;                                  // short runs over NVLink: last resort
+      cand.push_back(c);
+    }
+    std::sort(cand.begin(), cand.end(), [](const Cand& a, const Cand& b) {
+      if (a.cls != b.cls) return a.cls < b.cls;
+      if (a.order != b.order) return a.order < b.order;
+      return a.pos > b.pos;
+    });
+    if (cand.size() < in_q.size()) return fail(QCSIM_ERR_BAD_ARG, "internal: no local partner for the exchange");
+    DistStep ex;
+    ex.exchange = true;
+    ex.k = (int)in_q.size();
+    for (int j = 0; j < ex.k; ++j) {
+      ex.gpos[j] = Lo.phys_of[in_q[j]];
+      ex.lpos[j] = cand[j].pos;
+    }
     QCSIM_TRY(do_exchange(h, ex));
-    QCSIM_TRY(engine_qft_passes(h, nl - gg, nl - 1, inverse, (uint64_t)h->rank << nl, seg, 2, gg, sq));
-    QCSIM_TRY(do_exchange(h, ex));
-    return QCSIM_OK;
-  };
-  if (!inverse) {
-    if (gg) QCSIM_TRY(top_pass());
-    QCSIM_TRY(engine_qft_passes(h, sq, leq, false, 0, &ident, 1, 0, sq));
-    if (do_swap) virtual_swaps();
-  } else {
-    QCSIM_TRY(engine_qft_passes(h, sq, leq, true, 0, &ident, 1, 0, sq));
-    if (gg) QCSIM_TRY(top_pass());
+    for (int j = 0; j < ex.k; ++j) Lo.swap_physical(ex.gpos[j], ex.lpos[j]);
   }
-  *handled = 1;
+  if (!inverse && do_swap) virtual_swaps();
   return QCSIM_OK;
 }
 

@@ -7,10 +7,11 @@
 // it starts as the identity (rank = top g qubits) and changes when
 //   * a SWAP gate is applied: pure relabelling, no data moves;
 //   * a gate needs non-diagonal access to a qubit that currently sits on a global position: the
-//     planner emits an EXCHANGE step that swaps k global positions with the top k local positions
-//     (an all-to-all among the 2^k ranks that differ in those bits; contiguous 2^(n_local-k)
-//     blocks, so no pack/unpack kernels), preceded by local SWAP passes that park the k local
-//     qubits whose next non-diagonal use is farthest away on those top positions.
+//     planner emits an EXCHANGE step that swaps k global positions with k local positions (an
+//     all-to-all among the 2^k ranks that differ in those bits).  The local partners are the
+//     positions of the k local qubits whose next non-diagonal use is farthest away -- wherever they
+//     sit: the exchange kernel moves strided runs of 2^(lowest partner position) amplitudes, so no
+//     local "parking" pass is needed (positions below kMinExchangePos are avoided: short runs).
 // Everything else is shard-local: controls on global positions are decided per rank (run or
 // skip), diagonal selectors on global positions are folded into the table.  The layout is only
 // brought back to the identity (dist_plan_canonicalize) when the caller looks at amplitudes.
@@ -49,12 +50,15 @@ struct DistLayout {
   bool is_global(int logical) const { return phys_of[logical] >= n_local; }
 };
 
+constexpr int kMaxExchange = 3;     // global positions per exchange = log2 of the largest world (engine.h: kMaxWorld = 8)
+constexpr int kMinExchangePos = 5;  // preferred lowest local partner position: runs of >= 2^5 amplitudes = 512 B
+
 struct DistStep {
   bool exchange = false;
   std::vector<Op> ops;  // !exchange: ops on physical LOCAL positions, folded for this rank
-  int k = 0;            // exchange: physical position gpos[j] <-> lpos[j] = n_local - k + j
-  int gpos[3] = {0, 0, 0};
-  int lpos[3] = {0, 0, 0};
+  int k = 0;            // exchange: physical position gpos[j] <-> lpos[j] (any distinct local positions)
+  int gpos[kMaxExchange] = {0, 0, 0};
+  int lpos[kMaxExchange] = {0, 0, 0};
 };
 
 namespace detail {
@@ -192,33 +196,23 @@ inline std::vector<DistStep> dist_plan(DistLayout& L, const std::vector<Op>& ops
         else if (!((nd[i] >> q) & 1ULL)) outgoing.push_back({nu, q});
       }
       std::sort(incoming.begin(), incoming.end());
-      // farthest next use first; ties: prefer the qubit already highest up (fewer local swaps)
+      // farthest next use first; positions below kMinExchangePos only when nothing else is left (short
+      // runs over NVLink); ties: the qubit highest up (longest contiguous runs)
+      const int min_pos = std::min(kMinExchangePos, std::max(0, nl - g - 1));
       std::sort(outgoing.begin(), outgoing.end(), [&](const std::pair<int, int>& a, const std::pair<int, int>& b) {
+        const bool la = L.phys_of[a.second] < min_pos, lb = L.phys_of[b.second] < min_pos;
+        if (la != lb) return lb;
         if (a.first != b.first) return a.first > b.first;
         return L.phys_of[a.second] > L.phys_of[b.second];
       });
       int k = 0;
       std::vector<int> in_q, out_q;
-      for (size_t j = 0; j < incoming.size() && j < outgoing.size() && (int)j < g; ++j) {
+      for (size_t j = 0; j < incoming.size() && j < outgoing.size() && (int)j < g && (int)j < kMaxExchange; ++j) {
         const bool mandatory = incoming[j].first == i;
         if (!mandatory && !(incoming[j].first < outgoing[j].first)) break;
         in_q.push_back(incoming[j].second);
         out_q.push_back(outgoing[j].second);
         ++k;
-      }
-      // park the outgoing qubits on the top k local positions
-      for (int j = 0; j < k; ++j) {
-        const int slot = nl - k + j;
-        const int occupant = L.log_of[slot];
-        if (std::find(out_q.begin(), out_q.end(), occupant) != out_q.end()) continue;
-        int mover = -1;
-        for (int v : out_q)
-          if (L.phys_of[v] < nl - k) {
-            mover = v;
-            break;
-          }
-        cur.ops.push_back(physical_swap_op(L.phys_of[mover], slot));
-        L.swap_physical(L.phys_of[mover], slot);
       }
       flush_local();
       DistStep ex;
@@ -226,7 +220,7 @@ inline std::vector<DistStep> dist_plan(DistLayout& L, const std::vector<Op>& ops
       ex.k = k;
       for (int j = 0; j < k; ++j) {
         ex.gpos[j] = L.phys_of[in_q[j]];
-        ex.lpos[j] = nl - k + j;
+        ex.lpos[j] = L.phys_of[out_q[j]];
       }
       steps.push_back(ex);
       for (int j = 0; j < k; ++j) L.swap_physical(ex.gpos[j], ex.lpos[j]);
@@ -246,64 +240,47 @@ inline std::vector<DistStep> dist_plan(DistLayout& L, const std::vector<Op>& ops
   return steps;
 }
 
-// Steps that bring the layout back to the identity (<= 2 exchanges + local SWAP passes).
+// Steps that bring the layout back to the identity: exchanges that put every global position's own
+// qubit back (a position whose qubit sits on another global position first trades with a plain local
+// one), then ONE local step of position swaps.
 inline std::vector<DistStep> dist_plan_canonicalize(DistLayout& L) {
   using namespace detail;
   const int nl = L.n_local, n = L.n;
   std::vector<DistStep> steps;
-  auto wrong_globals = [&]() {
-    std::vector<int> w;
-    for (int p = nl; p < n; ++p)
-      if (L.log_of[p] != p) w.push_back(p);
-    return w;
-  };
-  auto do_exchange = [&](const std::vector<int>& gp) {
+  auto do_exchange = [&](const std::vector<int>& gp, const std::vector<int>& lp) {
     DistStep ex;
     ex.exchange = true;
     ex.k = (int)gp.size();
     for (int j = 0; j < ex.k; ++j) {
       ex.gpos[j] = gp[j];
-      ex.lpos[j] = nl - ex.k + j;
+      ex.lpos[j] = lp[j];
     }
     steps.push_back(ex);
     for (int j = 0; j < ex.k; ++j) L.swap_physical(ex.gpos[j], ex.lpos[j]);
   };
-  std::vector<int> w = wrong_globals();
-  if (!w.empty()) {
-    // phase A: qubits that belong on a global position but sit on ANOTHER global position come
-    // down first, traded against local qubits that have no business up there
-    std::vector<int> stray;
-    for (int p : w)
-      if (L.log_of[p] >= nl) stray.push_back(p);
-    if (!stray.empty()) {
-      const int a = (int)stray.size();
-      DistStep park;
-      for (int j = 0; j < a; ++j) {
-        const int slot = nl - a + j;
-        if (L.log_of[slot] < nl) continue;  // already a plain local qubit
-        int donor = -1;
-        for (int x = 0; x < nl - a; ++x)
-          if (L.log_of[x] < nl) {
-            donor = x;
-            break;
-          }
-        park.ops.push_back(physical_swap_op(donor, slot));
-        L.swap_physical(donor, slot);
+  for (int guard = 0; guard < 8; ++guard) {
+    std::vector<int> gp, lp;
+    bool any_wrong = false;
+    for (int p = nl; p < n; ++p) {
+      if (L.log_of[p] == p) continue;
+      any_wrong = true;
+      if (L.phys_of[p] < nl && (int)gp.size() < kMaxExchange) {  // its own qubit is local: bring it up
+        gp.push_back(p);
+        lp.push_back(L.phys_of[p]);
       }
-      if (!park.ops.empty()) steps.push_back(park);
-      do_exchange(stray);
     }
-    w = wrong_globals();
-    const int k = (int)w.size();
-    DistStep loc;
-    for (int j = 0; j < k; ++j) {
-      const int slot = nl - k + j;
-      if (L.log_of[slot] == w[j]) continue;
-      loc.ops.push_back(physical_swap_op(L.phys_of[w[j]], slot));
-      L.swap_physical(L.phys_of[w[j]], slot);
+    if (!any_wrong) break;
+    if (gp.empty()) {
+      // every wrong global position wants a qubit that sits on another global position: break the cycle by
+      // trading one of them against a local position that holds a local qubit (highest such position)
+      int p = nl;
+      while (L.log_of[p] == p) ++p;
+      int x = nl - 1;
+      while (x >= 0 && L.log_of[x] >= nl) --x;
+      gp.push_back(p);
+      lp.push_back(x);
     }
-    if (!loc.ops.empty()) steps.push_back(loc);
-    if (k) do_exchange(w);
+    do_exchange(gp, lp);
   }
   DistStep loc;
   for (int p = 0; p < nl; ++p) {

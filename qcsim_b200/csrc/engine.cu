@@ -468,21 +468,25 @@ static void item_bit_order(int k, uint32_t reg_mask, uint32_t* words, int n_word
   for (int j = 0; j < n && j < 4 * n_words; ++j) words[j >> 2] |= (uint32_t)order[j] << (8 * (j & 3));
 }
 
-// QFT / IQFT on the LOCAL physical positions [sq, eq] as radix-8 FFT passes (qft_kernels.cuh).
-// `seg` maps a physical index (local bits | rank_bits) to the logical value of the qubits, for
-// the twiddle exponent; on one GPU it is the identity.
-int engine_qft_passes(qcsim_sv* h, int sq, int eq, bool inverse, uint64_t rank_bits, const QftSegment* seg, int n_seg,
-                      int logical_shift, int r_floor) {
+// The QFT / IQFT gates whose TARGET is one of the logical qubits [lo, hi], as radix-8 FFT passes
+// (qft_kernels.cuh).  [lo, hi] is a slice of a transform that starts at logical qubit r_floor (the twiddles read
+// every lower qubit down to r_floor, wherever it lives: local bits, or rank bits on a sharded register).
+// phys_of maps logical qubits to physical index bits (nullptr: identity); the qubits [lo, hi] must sit on local
+// positions, in any order.
+int engine_qft_passes(qcsim_sv* h, int lo, int hi, bool inverse, int r_floor, const int* phys_of) {
   const int nl = h->n_local;
-  const int m = eq - sq + 1;
+  int ident[64];
+  if (!phys_of) {
+    for (int q = 0; q < 64; ++q) ident[q] = q;
+    phys_of = ident;
+  }
   struct Grp { int top, size; };
   std::vector<Grp> groups;  // top-down
-  for (int top = eq; top >= sq;) {
-    const int size = std::min(3, top - sq + 1);
+  for (int top = hi; top >= lo;) {
+    const int size = std::min(3, top - lo + 1);
     groups.push_back({top, size});
     top -= size;
   }
-  (void)m;
   const int Kmax = std::min(kMaxTileBits, nl);
   const int Lmin = std::min(3, nl);
   struct Pass { std::vector<int> tile; std::vector<Grp> groups; };
@@ -492,7 +496,11 @@ int engine_qft_passes(qcsim_sv* h, int sq, int eq, bool inverse, uint64_t rank_b
     Pass p;
     while (i < groups.size() && (int)p.groups.size() < kMaxQftGroups) {
       uint64_t gb = 0;
-      for (int j = 0; j < groups[i].size; ++j) gb |= 1ULL << (groups[i].top - j);
+      for (int j = 0; j < groups[i].size; ++j) {
+        const int ph = phys_of[groups[i].top - j];
+        if (ph < 0 || ph >= nl) return fail(QCSIM_ERR_BAD_ARG, "internal: QFT target qubit is not on a local position");
+        gb |= 1ULL << ph;
+      }
       if (__builtin_popcountll(bits | gb) > Kmax) break;
       bits |= gb;
       p.groups.push_back(groups[i]);
@@ -520,30 +528,39 @@ int engine_qft_passes(qcsim_sv* h, int sq, int eq, bool inverse, uint64_t rank_b
     A.n_groups = (int)p.groups.size();
     A.inverse = inverse ? 1 : 0;
     A.n_tiles = 1ULL << (nl - k);
-    A.rank_bits = rank_bits;
+    A.rank_bits = (uint64_t)h->rank << nl;
     for (int j = 0; j < kMaxTileBits; ++j) A.tpos[j] = j < k ? p.tile[j] : 0;
     A.sq = r_floor;  // logical start qubit of the whole transform
-    A.n_seg = n_seg;
-    for (int i = 0; i < n_seg; ++i) A.seg[i] = seg[i];
+    A.n_phys = h->n;
+    for (int q = 0; q < h->n; ++q) A.log_of[phys_of[q]] = (signed char)q;
     A.s = 1. / std::sqrt(2.);
     const double sign = inverse ? -1.0 : 1.0;
     A.ph2 = make_amp(std::cos(sign * pi / 2), std::sin(sign * pi / 2));  // std::polar(1., theta)
     A.ph4 = make_amp(std::cos(sign * pi / 4), std::sin(sign * pi / 4));
+    int local_of[64];
+    for (int q = 0; q < 64; ++q) local_of[q] = -1;
+    for (int j = 0; j < k; ++j) local_of[p.tile[j]] = j;
     for (size_t g = 0; g < p.groups.size(); ++g) {
       QftGroup& G = A.groups[g];
       G.size = p.groups[g].size;
-      G.top_qubit = p.groups[g].top + logical_shift;
+      G.top_qubit = p.groups[g].top;
       const int low_q = p.groups[g].top - G.size + 1;
-      int lbit = 0;
-      while (p.tile[lbit] != low_q) ++lbit;
-      G.lbit = lbit;
-      const uint32_t reg_mask = ((1u << G.size) - 1u) << lbit;
+      uint32_t reg_mask = 0;
+      G.rb = 0;
+      for (int j = 0; j < G.size; ++j) {
+        const int lb = local_of[phys_of[low_q + j]];
+        G.rb |= (uint32_t)lb << (8 * j);
+        reg_mask |= 1u << lb;
+      }
       item_bit_order(k, reg_mask, G.tb, 3);
     }
     const size_t smem = (sizeof(amp) << k) + sizeof(amp) * kMaxQftGroups;
     const uint64_t grid = std::min<uint64_t>(A.n_tiles, (uint64_t)kNumSMs * 3);
-    if (!h->d_qft_table) CUDA_TRY(cudaMalloc(&h->d_qft_table, sizeof(amp) * kMaxQftGroups * kQftItems3));
-    if (k == 12) k_qft_item_table<<<kMaxQftGroups * kQftItems3 / 256, 256, 0, h->stream>>>(h->d_qft_table, A);
+    if (!h->d_qft_table) CUDA_TRY(cudaMalloc(&h->d_qft_table, sizeof(amp) * kMaxQftGroups * kQftItemsMax));
+    if (k == 12) {
+      k_qft_item_table<<<kMaxQftGroups * kQftItemsMax / 256, 256, 0, h->stream>>>(h->d_qft_table, A);
+      h->stats.kernel_launches += 1;
+    }
     k_qft_pass<<<(unsigned)grid, kTileThreads, smem, h->stream>>>(h->psi, h->d_qft_table, A);
     CUDA_TRY(cudaGetLastError());
     count_pass(h, h->dim_local);
@@ -719,9 +736,8 @@ int engine_qft_direct(qcsim_sv* h, int sq, int eq, bool do_swap, bool inverse) {
     // transform entirely on global qubits: expand and run through the sharded gate path
     return dist_execute(h, qft_gate_ops(sq, eq, do_swap, inverse));
   }
-  const QftSegment ident = {0, h->n, 0, 0};
   if (inverse && do_swap) QCSIM_TRY(engine_reverse_bits(h, sq, eq));
-  QCSIM_TRY(engine_qft_passes(h, sq, eq, inverse, 0, &ident, 1, 0, sq));
+  QCSIM_TRY(engine_qft_passes(h, sq, eq, inverse, sq, nullptr));
   if (!inverse && do_swap) QCSIM_TRY(engine_reverse_bits(h, sq, eq));
   return QCSIM_OK;
 }

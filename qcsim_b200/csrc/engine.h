@@ -100,9 +100,7 @@ int engine_flush(qcsim_sv* h);
 void engine_drop_queue(qcsim_sv* h);
 int engine_canonicalize(qcsim_sv* h);
 int engine_qft(qcsim_sv* h, uint64_t sq, uint64_t eq, bool do_swap, bool inverse);
-struct QftSegment;
-int engine_qft_passes(qcsim_sv* h, int sq, int eq, bool inverse, uint64_t rank_bits, const QftSegment* seg, int n_seg,
-                      int logical_shift, int r_floor);
+int engine_qft_passes(qcsim_sv* h, int lo, int hi, bool inverse, int r_floor, const int* phys_of);
 int engine_permute_bits(qcsim_sv* h, const int* src_of);
 int engine_reverse_bits(qcsim_sv* h, int sq, int eq);
 int engine_qft_direct(qcsim_sv* h, int sq, int eq, bool do_swap, bool inverse);

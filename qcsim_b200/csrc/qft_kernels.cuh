@@ -28,16 +28,11 @@ constexpr int kMaxQftGroups = 4;
 
 struct QftGroup {
   int size;         // 1..3 qubits
-  int lbit;         // tile-local bit of the group's lowest qubit (the others follow)
   int top_qubit;    // logical index of the group's highest qubit (c2)
+  uint32_t rb;      // tile-local bit of the group's qubits, lowest logical first (byte each)
   int pad;
   uint32_t tb[3];   // tile bit walked by item-index bit j (byte each), for the k - size other bits
   uint32_t pad2;
-};
-
-// logical value of the lower qubits = sum over segments ((phys >> from) & ((1 << len) - 1)) << to
-struct QftSegment {
-  int from, len, to, pad;
 };
 
 struct QftPassArgs {
@@ -48,9 +43,10 @@ struct QftPassArgs {
   uint64_t n_tiles;
   uint64_t rank_bits;    // physical index bits above the local slice (rank << n_local), 0 on one GPU
   int tpos[kMaxTileBits];
-  int sq;                // lowest qubit of the transform: bits below it never enter R
-  int n_seg;
-  QftSegment seg[4];     // physical index -> logical value of the qubits (for R)
+  int sq;                // lowest (logical) qubit of the transform: bits below it never enter R
+  int n_phys;            // physical index bits (local + rank bits)
+  signed char log_of[64];  // logical qubit held by physical index bit p: any layout (sharded registers keep qubit
+                           // reversals and exchanges virtual, dist.cu) -- R is gathered bit by bit
   double s;              // 1/sqrt(2), HadamardGate (SimpleGates.h:588-596)
   double2 ph2, ph4;      // std::polar(1., +-pi/2), std::polar(1., +-pi/4) (QuantumGate.h:262-265), sign by direction
   QftGroup groups[kMaxQftGroups];
@@ -126,13 +122,12 @@ __device__ __forceinline__ void qft_group(amp (&v)[8], const QftPassArgs& A, boo
 // of the twiddles of 3-qubit groups in 12-bit tiles depends on the item only: it is tabulated once
 // per pass in global memory (k_qft_item_table, 32 KiB, L1-resident) so that the tile kernel fits
 // three CTAs per SM.
-constexpr int kQftItems3 = 512;  // items of a 3-qubit group in a 12-bit tile
+constexpr int kQftItemsMax = 2048;  // items of a 1-qubit group in a 12-bit tile (512 for a 3-qubit group)
 
 __device__ __forceinline__ uint64_t qft_logical(const QftPassArgs& A, uint64_t phys) {
   uint64_t logical = 0;
-#pragma unroll
-  for (int sgi = 0; sgi < 4; ++sgi)
-    if (sgi < A.n_seg) logical |= ((phys >> A.seg[sgi].from) & ((1ULL << A.seg[sgi].len) - 1ULL)) << A.seg[sgi].to;
+#pragma unroll 1
+  for (int p = 0; p < A.n_phys; ++p) logical |= ((phys >> p) & 1ULL) << A.log_of[p];
   return logical;
 }
 
@@ -161,14 +156,15 @@ __device__ __forceinline__ uint64_t qft_phys_of_local(const QftPassArgs& A, uint
   return phys;
 }
 
-// table[g * 512 + item] = thread part of the twiddle base of item `item` of group g (12-bit tiles)
+// table[g * kQftItemsMax + item] = thread part of the twiddle base of item `item` of group g (12-bit tiles)
 static __global__ void k_qft_item_table(amp* __restrict__ table, const __grid_constant__ QftPassArgs A) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int gi = i / kQftItems3;
+  const int gi = i / kQftItemsMax;
   if (gi >= A.n_groups) return;
   const QftGroup grp = A.groups[gi];
-  if (grp.size != 3) return;
-  const uint32_t lbase = qft_lbase(grp, i % kQftItems3);
+  const uint32_t item = i % kQftItemsMax;
+  if (item >= (1u << (A.k - grp.size))) return;
+  const uint32_t lbase = qft_lbase(grp, item);
   table[i] = qft_base(A, grp, qft_logical(A, qft_phys_of_local(A, lbase)), A.inverse != 0);
 }
 
@@ -228,14 +224,14 @@ static __global__ void __launch_bounds__(kTileThreads, 3) k_qft_pass(amp* __rest
       const QftGroup grp = A.groups[gi];
       const int G = grp.size;
       const uint32_t items = tile_amps >> G;
-      const uint32_t so0 = swz(1u << grp.lbit), so1 = swz(2u << grp.lbit), so2 = swz(4u << grp.lbit);
+      const uint32_t so0 = swz(1u << (grp.rb & 31u)), so1 = swz(1u << ((grp.rb >> 8) & 31u)), so2 = swz(1u << ((grp.rb >> 16) & 31u));
       const amp p_cta = tw_cta[gi];
 #pragma unroll 1
       for (uint32_t item = tid; item < items; item += kTileThreads) {
         const uint32_t lbase = qft_lbase(grp, item);
         amp P;
-        if (tabled && G == 3) {
-          P = cmul(p_cta, __ldg(tw_item + gi * kQftItems3 + item));
+        if (tabled) {
+          P = cmul(p_cta, __ldg(tw_item + gi * kQftItemsMax + item));
         } else {
           P = qft_base(A, grp, qft_logical(A, gbase | A.rank_bits | qft_phys_of_local(A, lbase)), inverse);
         }

@@ -104,6 +104,25 @@ def main():
             assert st0["exchange_calls"] >= 1 and st0["exchange_bytes"] > 0
         reg.close()
 
+    # chained transforms without looking at the state in between: the register stays in whatever layout the
+    # previous transform left (virtual qubit reversal, exchanged qubits) -- nothing is canonicalised
+    for n in (12, 17):
+        psi0 = random_state(n, 9)
+        reg = create_register(n, local, rank, world, dist)
+        with oracle.best_oracle(n) as ref:
+            ref.set_state(psi0)
+            reg.upload_slice(slice_of(psi0, reg))
+            reg.reset_stats()
+            for args in ((0, n - 1, True, False), (0, n - 1, True, False), (1, n - 2, True, True), (0, n - 1, False, False),
+                         (0, n - 1, True, True), (2, n - 1, False, True)):
+                ref.qft(*args)
+                reg.QFT(*args)
+            passes = reg.stats()["state_passes"]
+            check_state(reg, ref, f"chained qft n={n}")
+            if rank == 0:
+                print(f"chained QFT n={n}: {passes} state passes for 6 transforms, {reg.stats()['exchange_calls']} exchanges", flush=True)
+        reg.close()
+
     # Grover with gates (config 4 shape, small): the n-controlled NOT ladders over all shards
     n_search = 5
     n = 2 * n_search - 1

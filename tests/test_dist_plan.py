@@ -47,8 +47,17 @@ def plan(hl, circ, n, n_local, rank, phys_of, canonicalize=False):
     return steps, list(po[:n])
 
 
+def sub_block(nl, lpos, v):
+    """local indices whose partner bits lpos hold the value v (ascending) -- the strided block k_exchange_swap trades"""
+    idx = np.arange(1 << nl)
+    keep = np.ones(1 << nl, dtype=bool)
+    for j, p in enumerate(lpos):
+        keep &= ((idx >> p) & 1) == ((v >> j) & 1)
+    return idx[keep]
+
+
 def exchange_blocks(rank, k, gpos, n_local):
-    """(peer, block) pairs rank exchanges: block t of my slice <-> block a of peer's (dist.cu do_exchange)"""
+    """(peer, t, a) triples of rank: my amplitudes with partner bits = t <-> the peer's with partner bits = a (dist.cu do_exchange)"""
     a = sum(((rank >> (gpos[j] - n_local)) & 1) << j for j in range(k))
     out = []
     for t in range(1 << k):
@@ -92,12 +101,11 @@ def run_sharded(hl, circ, n, world, psi):
             ex = [plans[r][cursors[r]] for r in range(world)]
             assert all(e == ex[0] for e in ex)
             _, k, gpos, lpos = ex[0]
-            assert lpos == [nl - k + j for j in range(k)]
-            blk = (1 << nl) >> k
+            assert len(set(lpos)) == k and all(0 <= p < nl for p in lpos) and all(nl <= p < n for p in gpos)
             new = [s.copy() for s in shards]
             for r in range(world):
                 for peer, t, a in exchange_blocks(r, k, gpos, nl):
-                    new[r][t * blk: (t + 1) * blk] = shards[peer][a * blk: (a + 1) * blk]
+                    new[r][sub_block(nl, lpos, t)] = shards[peer][sub_block(nl, lpos, a)]
             shards = new
             n_exch += 1
             for r in range(world):
@@ -195,18 +203,17 @@ for phase in (circ, None):
                 mine = test_planner.apply_op(mine, op, nl)
         else:
             _, k, gpos, lpos = s
-            blk = (1 << nl) >> k
             new = mine.copy()
             reqs, bufs = [], []
             for peer, t, a in test_dist_plan.exchange_blocks(rank, k, gpos, nl):
-                send = torch.from_numpy(np.ascontiguousarray(mine[t * blk:(t + 1) * blk]).view(np.float64).copy())
+                send = torch.from_numpy(np.ascontiguousarray(mine[test_dist_plan.sub_block(nl, lpos, t)]).view(np.float64).copy())
                 recv = torch.empty_like(send)
                 reqs += [dist.isend(send, peer), dist.irecv(recv, peer)]
                 bufs.append((t, recv, send))
             for r in reqs:
                 r.wait()
             for t, recv, _ in bufs:
-                new[t * blk:(t + 1) * blk] = recv.numpy().view(np.complex128)
+                new[test_dist_plan.sub_block(nl, lpos, t)] = recv.numpy().view(np.complex128)
             mine = new
 want = test_dist_plan.run_unsharded(circ, n, psi)[rank << nl: (rank + 1) << nl]
 err = float(np.max(np.abs(mine - want)))
