@@ -118,6 +118,14 @@ class RefOracle(_Base):
         L.ref_grover_gates.argtypes = [C.c_int, _U64, _VP, C.POINTER(_U64)]
         L.ref_draper_add.argtypes = [C.c_int, _U64, _U64, _VP]
         L.ref_draws.argtypes = [_VP, _U64, C.c_int, _VP]
+        L.ref_repeated_measure.restype = C.c_int
+        L.ref_repeated_measure.argtypes = [_VP, _U64, _U64, C.c_int, _U64, _U64, _VP, _VP, C.c_int]
+        L.ref_state_fidelity.restype = C.c_double
+        L.ref_state_fidelity.argtypes = [_VP, _VP, _U64]
+        L.ref_expectation_value.argtypes = [_VP, C.c_int, _VP, _VP, _VP, _VP]
+        L.ref_save_state.argtypes = [_VP]
+        L.ref_restore_state.argtypes = [_VP, C.c_int]
+        L.ref_apply_operator_matrix.argtypes = [_VP, _VP]
         self.L = L
         self.n = n
         self.dim = 1 << n
@@ -230,6 +238,40 @@ class RefOracle(_Base):
         self.L.ref_draws(self.h, seed, count, out.ctypes.data_as(_VP))
         return out
 
+    def repeated_measure(self, seed: int, nr_times: int, first=None, last=None, unordered=False) -> dict:
+        """RepeatedMeasure[Unordered](nrTimes) / (first, last, nrTimes) after rng.seed(seed) (QubitRegister.h:227-429)"""
+        cap = max(16, min(nr_times, 1 << 20) + 1)
+        keys = np.zeros(cap, dtype=np.uint64)
+        counts = np.zeros(cap, dtype=np.uint64)
+        f, l = (1, 0) if first is None else (first, last)
+        n = self.L.ref_repeated_measure(self.h, seed, nr_times, int(unordered), f, l, keys.ctypes.data_as(_VP), counts.ctypes.data_as(_VP), cap)
+        assert n <= cap
+        return {int(k): int(c) for k, c in zip(keys[:n], counts[:n])}
+
+    def state_fidelity(self, state) -> float:
+        v = _as_f64(state)
+        return self.L.ref_state_fidelity(self.h, v.ctypes.data_as(_VP), v.size)
+
+    def expectation_value(self, circuit) -> complex:
+        """ExpectationValue(gates) with gates given as (gate, q, c1, c2) tuples (flag-less AppliedGates, :646-660)"""
+        nq = (C.c_int * len(circuit))(*[g.nq for g, *_ in circuit])
+        mats = np.concatenate([np.ascontiguousarray(g.matrix, dtype=np.complex128).ravel() for g, *_ in circuit]).view(np.float64)
+        qs = np.array([[q, c1, c2] for _, q, c1, c2 in circuit], dtype=np.uint64).ravel()
+        out = np.zeros(2)
+        self._rc(self.L.ref_expectation_value(self.h, len(circuit), nq, mats.ctypes.data_as(_VP), qs.ctypes.data_as(_VP), out.ctypes.data_as(_VP)))
+        return complex(out[0], out[1])
+
+    def save_state(self):
+        self.L.ref_save_state(self.h)
+
+    def restore_state(self, destructive=False):
+        self.L.ref_restore_state(self.h, int(destructive))
+
+    def apply_operator_matrix(self, m) -> None:
+        m = np.ascontiguousarray(m, dtype=np.complex128)
+        assert m.shape == (self.dim, self.dim)
+        self._rc(self.L.ref_apply_operator_matrix(self.h, m.ctypes.data_as(_VP)))
+
     def grover_gates(self, n_search: int, marked: int) -> np.ndarray:
         nq = 2 * n_search - 1
         out = np.empty(1 << nq, dtype=np.complex128)
@@ -333,9 +375,15 @@ class PortOracle(_Base):
 
 
 def best_oracle(n: int, variant: str = "sse2") -> _Base:
+    """The compiled reference when it is available, else the C port.  With QCSIM_REQUIRE_REF=1 (set by the GPU
+    parity tests) there is no silent fallback: a missing reference build is an error."""
     if ref_available(variant):
         try:
             return RefOracle(n, variant)
         except OSError:
-            pass
+            if os.environ.get("QCSIM_REQUIRE_REF"):
+                raise
+    if os.environ.get("QCSIM_REQUIRE_REF"):
+        raise RuntimeError("oracle/_ref (the compiled reference) is required for the GPU parity tests but is not available; "
+                           "build it where /root/reference exists (python -c 'import oracle; oracle.build_ref()')")
     return PortOracle(n)

@@ -250,6 +250,76 @@ uint64_t ref_measure_nocollapse(void* h, uint64_t first, uint64_t last, double p
   return r->measureNoCollapseRange(first, last);
 }
 
+// RepeatedMeasure / RepeatedMeasureUnordered, whole register or [first, last] (QubitRegister.h:227-429), after
+// rng.seed(seed).  variant: 0 ordered, 1 unordered; first > last: the whole-register overloads.  Writes up to `cap`
+// (outcome, count) pairs sorted by outcome; returns the number of distinct outcomes.
+int ref_repeated_measure(void* h, uint64_t seed, uint64_t nr_times, int variant, uint64_t first, uint64_t last, uint64_t* keys, uint64_t* counts,
+                         int cap) {
+  RefRegister* r = static_cast<RefRegister*>(h);
+  r->reseed(seed);
+  std::map<size_t, size_t> out;
+  if (first > last) {
+    if (variant == 0) out = r->RepeatedMeasure(nr_times);
+    else for (const auto& kv : r->RepeatedMeasureUnordered(nr_times)) out[kv.first] = kv.second;
+  } else {
+    if (variant == 0) out = r->RepeatedMeasure(first, last, nr_times);
+    else for (const auto& kv : r->RepeatedMeasureUnordered(first, last, nr_times)) out[kv.first] = kv.second;
+  }
+  int i = 0;
+  for (const auto& kv : out) {
+    if (i < cap) {
+      keys[i] = kv.first;
+      counts[i] = kv.second;
+    }
+    ++i;
+  }
+  return i;
+}
+
+// stateFidelity (QubitRegister.h:527-534) against a caller-supplied state
+double ref_state_fidelity(void* h, const double* state, uint64_t dim) {
+  RefRegister* r = static_cast<RefRegister*>(h);
+  Vec v(dim);
+  std::memcpy(v.data(), state, sizeof(double) * 2 * dim);
+  return r->stateFidelity(v);
+}
+
+// ExpectationValue (QubitRegister.h:646-660) of a product of gates given as (nq, row-major matrix, q, c1, c2) records
+int ref_expectation_value(void* h, int n_gates, const int* nq, const double* mats, const uint64_t* qubits, double* out_re_im) {
+  RefRegister* r = static_cast<RefRegister*>(h);
+  return guarded([&] {
+    std::vector<QC::Gates::AppliedGate<Mat>> gates;
+    size_t off = 0;
+    for (int i = 0; i < n_gates; ++i) {
+      gates.emplace_back(fromRowMajor(nq[i], mats + off), qubits[3 * i], qubits[3 * i + 1], qubits[3 * i + 2]);
+      off += 2 * (size_t(1) << nq[i]) * (size_t(1) << nq[i]);
+    }
+    const std::complex<double> v = r->ExpectationValue(gates);
+    out_re_im[0] = v.real();
+    out_re_im[1] = v.imag();
+  });
+}
+
+// SaveState / RestoreState / RestoreStateDestructive (QubitRegister.h:600-616)
+void ref_save_state(void* h) { static_cast<RefRegister*>(h)->SaveState(); }
+void ref_restore_state(void* h, int destructive) {
+  RefRegister* r = static_cast<RefRegister*>(h);
+  if (destructive) r->RestoreStateDestructive();
+  else r->RestoreState();
+}
+
+// ApplyOperatorMatrix (QubitRegister.h:499-505): dense 2^n x 2^n operator, row-major
+int ref_apply_operator_matrix(void* h, const double* m) {
+  RefRegister* r = static_cast<RefRegister*>(h);
+  return guarded([&] {
+    const size_t d = r->getNrBasisStates();
+    Mat M(d, d);
+    for (size_t i = 0; i < d; ++i)
+      for (size_t j = 0; j < d; ++j) M(i, j) = std::complex<double>(m[2 * (i * d + j)], m[2 * (i * d + j) + 1]);
+    r->ApplyOperatorMatrix(M);
+  });
+}
+
 // rng.seed(seed) then `count` draws of `1. - uniformZeroOne(rng)`: pins qcsim_b200/rng.py
 void ref_draws(void* h, uint64_t seed, int count, double* out) {
   RefRegister* r = static_cast<RefRegister*>(h);

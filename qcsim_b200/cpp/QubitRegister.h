@@ -221,10 +221,14 @@ namespace QC {
 			return static_cast<size_t>(out);
 		}
 
-		// :227-273: nrTimes draws against ONE cumulative table, built and searched on the device
+		// :227-273: nrTimes draws against ONE cumulative table.  The table is the reference's sequential running sum,
+		// reproduced bit for bit on the device, including its cut at 1 - epsilon and the end() outcome (:250-254, 268);
+		// a single shot takes the reference's MeasureNoCollapse shortcut (:231-236)
 		std::map<size_t, size_t> RepeatedMeasure(size_t nrTimes = 1000)
 		{
 			std::map<size_t, size_t> measurements;
+			if (nrTimes == 0) return measurements;
+			if (nrTimes == 1) { ++measurements[MeasureNoCollapse()]; return measurements; }
 			for (uint64_t s : SampleStates(nrTimes)) ++measurements[static_cast<size_t>(s)];
 			return measurements;
 		}
@@ -232,6 +236,8 @@ namespace QC {
 		std::unordered_map<size_t, size_t> RepeatedMeasureUnordered(size_t nrTimes = 1000)  // :276-322
 		{
 			std::unordered_map<size_t, size_t> measurements;
+			if (nrTimes == 0) return measurements;
+			if (nrTimes == 1) { ++measurements[MeasureNoCollapse()]; return measurements; }
 			for (uint64_t s : SampleStates(nrTimes)) ++measurements[static_cast<size_t>(s)];
 			return measurements;
 		}
@@ -239,7 +245,14 @@ namespace QC {
 		std::map<size_t, size_t> RepeatedMeasure(size_t firstQubit, size_t secondQubit, size_t nrTimes = 1000)  // :325-375
 		{
 			std::map<size_t, size_t> measurements;
+			if (nrTimes == 0) return measurements;
 			const size_t mask = MeasuredMask(firstQubit, secondQubit);
+			if (nrTimes == 1)  // :334-339: the already shifted outcome is masked and shifted once more, as in the reference
+			{
+				const size_t meas = MeasureNoCollapse(firstQubit, secondQubit);
+				++measurements[(meas & mask) >> firstQubit];
+				return measurements;
+			}
 			for (uint64_t s : SampleStates(nrTimes)) ++measurements[(static_cast<size_t>(s) & mask) >> firstQubit];
 			return measurements;
 		}
@@ -247,7 +260,14 @@ namespace QC {
 		std::unordered_map<size_t, size_t> RepeatedMeasureUnordered(size_t firstQubit, size_t secondQubit, size_t nrTimes = 1000)  // :378-429
 		{
 			std::unordered_map<size_t, size_t> measurements;
+			if (nrTimes == 0) return measurements;
 			const size_t mask = MeasuredMask(firstQubit, secondQubit);
+			if (nrTimes == 1)
+			{
+				const size_t meas = MeasureNoCollapse(firstQubit, secondQubit);
+				++measurements[(meas & mask) >> firstQubit];
+				return measurements;
+			}
 			for (uint64_t s : SampleStates(nrTimes)) ++measurements[(static_cast<size_t>(s) & mask) >> firstQubit];
 			return measurements;
 		}

@@ -670,70 +670,67 @@ void dist_collect_stats(qcsim_sv* h) {
   harvest_timings(h, true);
 }
 
-// ---- measurement scan over all ranks (layout is canonical here) -----------------------------------
+// ---- measurement scan over all ranks (layout is canonical here; engine.cu: engine_resolve_draws) -------------
 
-int dist_pick_state(qcsim_sv* h, double prob, uint64_t fallback, uint64_t* outcome) {
-  const int W = h->world;
-  const int g = (int)std::min<uint64_t>(h->n_chunks, (uint64_t)kNumSMs * 8);
-  ScanResult* res = (ScanResult*)h->h_pinned;
-  // 1. exact mass of every rank's slice
-  k_chunk_sums<<<g, kThreads, 0, h->stream>>>(h->psi, h->dim_local, h->n_chunks, h->d_chunk_sums);
-  k_find_chunk<<<1, 1024, 0, h->stream>>>(h->d_chunk_sums, h->n_chunks, dd_make(0, 0), 2.0, h->d_scan);  // prob 2: totals only
+// exact (double-double) probability mass held by the ranks below this one; k_chunk_sums has been queued
+int dist_scan_offset(qcsim_sv* h, dd* offset) {
+  k_chunk_prefix<<<1, 1024, 0, h->stream>>>(h->d_chunk_sums, h->n_chunks, dd_make(0, 0), h->d_prefix_hi, h->d_total);
   CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaMemcpyAsync(res, h->d_scan, sizeof(ScanResult), cudaMemcpyDeviceToHost, h->stream));
+  h->stats.kernel_launches += 1;
+  dd* tot = (dd*)h->h_pinned;
+  CUDA_TRY(cudaMemcpyAsync(tot, h->d_total, sizeof(dd), cudaMemcpyDeviceToHost, h->stream));
   QCSIM_TRY(engine_wait(h));
-  h->stats.kernel_launches += 2;
-  h->stats.state_passes += 1;
-  h->stats.bytes_moved += 16ULL * h->dim_local;
-  double mine[2] = {res->total.hi, res->total.lo};
-  double all[256];
+  double mine[2] = {tot->hi, tot->lo};
+  double all[2 * kMaxWorld];
   QCSIM_TRY(allgather_host(h, mine, 2, all));
-  dd offset = dd_make(0, 0);
-  for (int r = 0; r < h->rank; ++r) offset = dd_add(offset, dd_make(all[2 * r], all[2 * r + 1]));
-  // 2. locate inside the slice, with the mass of the lower ranks as the starting prefix
-  k_find_chunk<<<1, 1024, 0, h->stream>>>(h->d_chunk_sums, h->n_chunks, offset, prob, h->d_scan);
-  k_find_in_chunk<<<1, kThreads, 0, h->stream>>>(h->psi, h->dim_local, prob, h->d_scan);
-  CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaMemcpyAsync(res, h->d_scan, sizeof(ScanResult), cudaMemcpyDeviceToHost, h->stream));
-  QCSIM_TRY(engine_wait(h));
-  h->stats.kernel_launches += 2;
-  double cand[2] = {res->found ? 1.0 : 0.0, res->found ? (double)(((uint64_t)h->rank << h->n_local) | res->index) : 0.0};
-  QCSIM_TRY(allgather_host(h, cand, 2, all));
-  uint64_t s = fallback;
-  for (int r = 0; r < W; ++r)
-    if (all[2 * r] != 0.0) {
-      s = (uint64_t)all[2 * r + 1];
-      break;
+  dd off = dd_make(0, 0);
+  for (int r = 0; r < h->rank; ++r) off = dd_add(off, dd_make(all[2 * r], all[2 * r + 1]));
+  *offset = off;
+  return QCSIM_OK;
+}
+
+// the reference's running sum continues from slice to slice: rank r walks its chunks starting from the sum rank r-1 ended with
+int dist_chained_walk(qcsim_sv* h) {
+  double acc = 0.0;
+  double* stage = (double*)h->h_pinned;
+  for (int r = 0; r < h->world; ++r) {
+    double out = 0.0;
+    if (r == h->rank) {
+      k_sequential_walk<<<1, kThreads, 0, h->stream>>>(h->psi, h->dim_local, h->n_chunks, h->d_prefix_hi, h->d_chunk_K, h->d_chunk_flags, acc,
+                                                       h->d_acc_start, nullptr);
+      CUDA_TRY(cudaGetLastError());
+      h->stats.kernel_launches += 1;
+      CUDA_TRY(cudaMemcpyAsync(stage, h->d_acc_start + h->n_chunks, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+      QCSIM_TRY(engine_wait(h));
+      out = *stage;
     }
-  if (h->strict_measure) {
-    // replay the reference's sequential fp64 sum rank by rank (QubitRegister.h:172-190)
-    unsigned long long* d_idx = (unsigned long long*)(h->d_scalars + 8);
-    double acc = 0.0;
-    s = fallback;
-    bool done = false;
-    for (int r = 0; r < W && !done; ++r) {
-      double out[2] = {0.0, 0.0};  // (found index + 1 or 0, running sum)
-      if (r == h->rank) {
-        k_sequential_scan<<<1, kThreads, 0, h->stream>>>(h->psi, h->dim_local, acc, prob, d_idx, h->d_scalars + 9);
-        CUDA_TRY(cudaGetLastError());
-        h->stats.kernel_launches += 1;
-        unsigned long long* stage = (unsigned long long*)((char*)h->h_pinned + 1024);
-        double* stage_acc = (double*)((char*)h->h_pinned + 1040);
-        CUDA_TRY(cudaMemcpyAsync(stage, d_idx, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
-        CUDA_TRY(cudaMemcpyAsync(stage_acc, h->d_scalars + 9, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-        QCSIM_TRY(engine_wait(h));
-        out[0] = (*stage == ~0ULL) ? 0.0 : (double)(*stage + 1);
-        out[1] = *stage_acc;
-      }
-      QCSIM_TRY(dist_allreduce_host(h, out, 2));  // only rank r contributed
-      if (out[0] != 0.0) {
-        s = ((uint64_t)r << h->n_local) | ((uint64_t)out[0] - 1);
-        done = true;
-      }
-      acc = out[1];
+    if (r + 1 < h->world) {
+      QCSIM_TRY(dist_allreduce_host(h, &out, 1));  // only rank r contributed
+      acc = out;
     }
   }
-  *outcome = s;
+  return QCSIM_OK;
+}
+
+static __global__ void k_outcomes_to_global(unsigned long long* o, uint64_t count, unsigned long long base) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) o[i] = (o[i] == ~0ULL) ? 0ULL : (base | o[i]) + 1ULL;  // 0 = not in this slice
+}
+static __global__ void k_outcomes_finish(unsigned long long* o, uint64_t count) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) o[i] = o[i] == 0ULL ? ~0ULL : o[i] - 1ULL;
+}
+
+// every draw is resolved by at most one rank (the running sums of the slices do not overlap): max over ranks
+int dist_combine_outcomes(qcsim_sv* h, unsigned long long* d_outcomes, uint64_t count) {
+  DistState* d = st(h);
+  QCSIM_TRY(spmd_note(h, 4, count));
+  const unsigned grid = (unsigned)((count + 255) / 256);
+  k_outcomes_to_global<<<grid, 256, 0, h->stream>>>(d_outcomes, count, (unsigned long long)h->rank << h->n_local);
+  NCCL_TRY(ncclAllReduce(d_outcomes, d_outcomes, count, ncclUint64, ncclMax, d->comm, h->stream));
+  k_outcomes_finish<<<grid, 256, 0, h->stream>>>(d_outcomes, count);
+  CUDA_TRY(cudaGetLastError());
+  h->stats.kernel_launches += 2;
   return QCSIM_OK;
 }
 

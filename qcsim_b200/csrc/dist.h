@@ -16,7 +16,9 @@ int dist_wait(qcsim_sv* h);  // bounded wait for the stream (a collective whose 
 int dist_allreduce_host(qcsim_sv* h, double* vals, int count);
 int dist_apply(qcsim_sv* h, const Op& op);
 int dist_canonicalize(qcsim_sv* h);
-int dist_pick_state(qcsim_sv* h, double prob, uint64_t fallback, uint64_t* outcome);
+int dist_scan_offset(qcsim_sv* h, dd* offset);
+int dist_chained_walk(qcsim_sv* h);
+int dist_combine_outcomes(qcsim_sv* h, unsigned long long* d_outcomes, uint64_t count);
 // fast QFT on a sharded register; *handled = 0 when the caller must fall back to the gate-by-gate path
 int dist_qft(qcsim_sv* h, int sq, int eq, bool do_swap, bool inverse, int* handled);
 void dist_collect_stats(qcsim_sv* h);  // resolves the CUDA-event timings of finished exchanges into stats.exchange_ms

@@ -97,7 +97,7 @@ int engine_create(qcsim_sv** out, int n_qubits, int device, int rank, int world,
   CREATE_TRY(cudaMalloc(&h->d_scalars, 64 * sizeof(double)));
   h->n_chunks = (h->dim_local + kChunk - 1) / kChunk;
   CREATE_TRY(cudaMalloc(&h->d_chunk_sums, h->n_chunks * sizeof(dd)));
-  CREATE_TRY(cudaMalloc(&h->d_scan, sizeof(ScanResult)));
+  CREATE_TRY(cudaMalloc(&h->d_total, sizeof(dd)));
   CREATE_TRY(cudaMallocHost(&h->h_pinned, 4096));
 #undef CREATE_TRY
   if (world > 1) {
@@ -119,7 +119,13 @@ int engine_destroy(qcsim_sv* h) {
   cudaFree(h->d_partials);
   cudaFree(h->d_scalars);
   cudaFree(h->d_chunk_sums);
-  cudaFree(h->d_scan);
+  cudaFree(h->d_total);
+  cudaFree(h->d_prefix_hi);
+  cudaFree(h->d_chunk_K);
+  cudaFree(h->d_chunk_flags);
+  cudaFree(h->d_acc_start);
+  cudaFree(h->d_draws);
+  cudaFree(h->d_outcomes);
   cudaFree(h->d_qft_table);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -744,75 +750,86 @@ int engine_qft_direct(qcsim_sv* h, int sq, int eq, bool do_swap, bool inverse) {
 
 // ---- measurement scan ----------------------------------------------------------------------------
 
-int engine_pick_state(qcsim_sv* h, double prob, uint64_t fallback, uint64_t* outcome) {
-  QCSIM_TRY(engine_canonicalize(h));
-  if (h->world > 1) return dist_pick_state(h, prob, fallback, outcome);
-  const int g = (int)std::min<uint64_t>(h->n_chunks, (uint64_t)kMaxPartials);
-  k_chunk_sums<<<g, kThreads, 0, h->stream>>>(h->psi, h->dim_local, h->n_chunks, h->d_chunk_sums);
-  k_find_chunk<<<1, 1024, 0, h->stream>>>(h->d_chunk_sums, h->n_chunks, dd_make(0, 0), prob, h->d_scan);
-  k_find_in_chunk<<<1, kThreads, 0, h->stream>>>(h->psi, h->dim_local, prob, h->d_scan);
-  CUDA_TRY(cudaGetLastError());
-  h->stats.kernel_launches += 3;
-  h->stats.state_passes += 1;
-  h->stats.bytes_moved += 16ULL * h->dim_local;
-  ScanResult* res = (ScanResult*)h->h_pinned;
-  CUDA_TRY(cudaMemcpyAsync(res, h->d_scan, sizeof(ScanResult), cudaMemcpyDeviceToHost, h->stream));
-  QCSIM_TRY(engine_wait(h));
-  uint64_t s = res->found ? res->index : fallback;
-  if (h->strict_measure) {
-    // replay the reference's sequential fp64 sum (QubitRegister.h:172-190) for a bit-identical outcome
-    unsigned long long* d_idx = (unsigned long long*)(h->d_scalars + 8);
-    k_sequential_scan<<<1, kThreads, 0, h->stream>>>(h->psi, h->dim_local, 0.0, prob, d_idx, h->d_scalars + 9);
-    CUDA_TRY(cudaGetLastError());
-    h->stats.kernel_launches += 1;
-    unsigned long long* stage = (unsigned long long*)((char*)h->h_pinned + 1024);
-    CUDA_TRY(cudaMemcpyAsync(stage, d_idx, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
-    QCSIM_TRY(engine_wait(h));
-    s = (*stage == ~0ULL) ? fallback : (uint64_t)*stage;
+static int ensure_scan_buffers(qcsim_sv* h, uint64_t count) {
+  if (!h->d_prefix_hi) {
+    CUDA_TRY(cudaMalloc(&h->d_prefix_hi, h->n_chunks * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&h->d_chunk_K, h->n_chunks * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMalloc(&h->d_chunk_flags, h->n_chunks * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&h->d_acc_start, (h->n_chunks + 1) * sizeof(double)));
   }
-  *outcome = s;
+  if (h->draws_capacity < count) {
+    cudaFree(h->d_draws);
+    cudaFree(h->d_outcomes);
+    h->d_draws = nullptr;
+    h->d_outcomes = nullptr;
+    h->draws_capacity = 0;
+    const uint64_t cap = std::max<uint64_t>(count, 1024);
+    CUDA_TRY(cudaMalloc(&h->d_draws, cap * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&h->d_outcomes, cap * sizeof(unsigned long long)));
+    h->draws_capacity = cap;
+  }
   return QCSIM_OK;
 }
 
-int engine_sample(qcsim_sv* h, const double* probs, uint64_t count, uint64_t* outcomes) {
-  // RepeatedMeasure (QubitRegister.h:227-273): many draws against ONE cumulative table.  The chunk
-  // masses (the only pass over the state) are computed once; every draw then costs two single-block
-  // kernels (scan of the chunk masses, scan inside the selected chunk) and 8 bytes back to the host.
+// The reference's running sum at every chunk start of this slice (reduce_kernels.cuh), then every draw resolved
+// against it.  On a sharded register the slices are chained: rank r starts from the sum rank r-1 ended with.
+int engine_resolve_draws(qcsim_sv* h, const double* probs, uint64_t count, uint64_t* outcomes) {
   if (count == 0) return QCSIM_OK;
   QCSIM_TRY(engine_canonicalize(h));
-  if (h->world > 1 || h->strict_measure) {
-    for (uint64_t i = 0; i < count; ++i) QCSIM_TRY(engine_pick_state(h, probs[i], 0, &outcomes[i]));
-    return QCSIM_OK;
-  }
+  QCSIM_TRY(ensure_scan_buffers(h, count));
   const int g = (int)std::min<uint64_t>(h->n_chunks, (uint64_t)kMaxPartials);
   k_chunk_sums<<<g, kThreads, 0, h->stream>>>(h->psi, h->dim_local, h->n_chunks, h->d_chunk_sums);
+  dd offset = dd_make(0, 0);
+  double start = 0.0;
+  if (h->world > 1) QCSIM_TRY(dist_scan_offset(h, &offset));  // exact mass of the lower ranks (binade prediction)
+  k_chunk_prefix<<<1, 1024, 0, h->stream>>>(h->d_chunk_sums, h->n_chunks, offset, h->d_prefix_hi, h->d_total);
+  k_chunk_increments<<<g, kThreads, 0, h->stream>>>(h->psi, h->dim_local, h->n_chunks, h->d_prefix_hi, h->d_chunk_K, h->d_chunk_flags);
+  CUDA_TRY(cudaGetLastError());
+  h->stats.kernel_launches += 3;
+  h->stats.state_passes += 2;
+  h->stats.bytes_moved += 32ULL * h->dim_local;
+  if (h->world > 1) {
+    QCSIM_TRY(dist_chained_walk(h));  // rank by rank: walk with the predecessor's final sum
+  } else {
+    k_sequential_walk<<<1, kThreads, 0, h->stream>>>(h->psi, h->dim_local, h->n_chunks, h->d_prefix_hi, h->d_chunk_K, h->d_chunk_flags, start,
+                                                     h->d_acc_start, nullptr);
+    CUDA_TRY(cudaGetLastError());
+    h->stats.kernel_launches += 1;
+  }
+  CUDA_TRY(cudaMemcpyAsync(h->d_draws, probs, count * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  k_resolve_draws<<<(unsigned)((count + 127) / 128), 128, 0, h->stream>>>(h->psi, h->dim_local, h->n_chunks, h->d_acc_start, h->d_draws, count,
+                                                                          h->d_outcomes);
   CUDA_TRY(cudaGetLastError());
   h->stats.kernel_launches += 1;
-  h->stats.state_passes += 1;
-  h->stats.bytes_moved += 16ULL * h->dim_local;
-  const uint64_t batch = 4096 / sizeof(ScanResult);  // results staged through the 4 KiB pinned buffer
-  ScanResult* d_res = nullptr;
-  CUDA_TRY(cudaMalloc(&d_res, batch * sizeof(ScanResult)));
-  ScanResult* stage = (ScanResult*)h->h_pinned;
-  int rc = QCSIM_OK;
-  for (uint64_t i0 = 0; i0 < count && rc == QCSIM_OK; i0 += batch) {
-    const uint64_t nb = std::min<uint64_t>(batch, count - i0);
-    for (uint64_t j = 0; j < nb; ++j) {
-      k_find_chunk<<<1, 1024, 0, h->stream>>>(h->d_chunk_sums, h->n_chunks, dd_make(0, 0), probs[i0 + j], d_res + j);
-      k_find_in_chunk<<<1, kThreads, 0, h->stream>>>(h->psi, h->dim_local, probs[i0 + j], d_res + j);
-    }
-    h->stats.kernel_launches += 2 * nb;
-    cudaError_t ce = cudaGetLastError();
-    if (ce == cudaSuccess) ce = cudaMemcpyAsync(stage, d_res, nb * sizeof(ScanResult), cudaMemcpyDeviceToHost, h->stream);
-    if (ce == cudaSuccess) ce = cudaStreamSynchronize(h->stream);
-    if (ce != cudaSuccess) {
-      rc = fail(QCSIM_ERR_CUDA, "sample: %s", cudaGetErrorString(ce));
-      break;
-    }
-    for (uint64_t j = 0; j < nb; ++j) outcomes[i0 + j] = stage[j].found ? stage[j].index : 0;  // fallback 0, QubitRegister.h:623
-  }
-  cudaFree(d_res);
-  return rc;
+  if (h->world > 1) QCSIM_TRY(dist_combine_outcomes(h, h->d_outcomes, count));  // local -> global index, one owner per draw
+  static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "outcome type");
+  CUDA_TRY(cudaMemcpyAsync(outcomes, h->d_outcomes, count * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
+  QCSIM_TRY(engine_wait(h));
+  return QCSIM_OK;
+}
+
+int engine_pick_state(qcsim_sv* h, double prob, uint64_t fallback, uint64_t* outcome) {
+  uint64_t s = 0;
+  QCSIM_TRY(engine_resolve_draws(h, &prob, 1, &s));
+  *outcome = (s == ~0ULL) ? fallback : s;
+  return QCSIM_OK;
+}
+
+// RepeatedMeasure (QubitRegister.h:227-273): `count` draws against ONE cumulative table.  The reference cuts its
+// table at the first index whose running sum exceeds 1 - DBL_EPSILON (:250-254) and std::lower_bound returns end()
+// for a draw above the last stored value (:268), i.e. the outcome "table size"; both are reproduced: the cut is one
+// more draw resolved against the same running sum.
+int engine_sample(qcsim_sv* h, const double* probs, uint64_t count, uint64_t* outcomes) {
+  if (count == 0) return QCSIM_OK;
+  std::vector<double> p(probs, probs + count);
+  const double cut_threshold = std::nextafter(1.0 - 2.220446049250313e-16, 2.0);  // first acc > 1 - eps  <=>  first acc >= the next double
+  p.push_back(cut_threshold);
+  std::vector<uint64_t> o(count + 1);
+  QCSIM_TRY(engine_resolve_draws(h, p.data(), count + 1, o.data()));
+  const uint64_t cut = o[count];
+  const uint64_t table_size = (cut == ~0ULL) ? h->dim : cut + 1;
+  for (uint64_t i = 0; i < count; ++i) outcomes[i] = (o[i] == ~0ULL || o[i] >= table_size) ? table_size : o[i];
+  return QCSIM_OK;
 }
 
 }  // namespace qcsim

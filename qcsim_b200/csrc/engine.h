@@ -30,7 +30,6 @@ int fail(int code, const char* fmt, ...);
                            cudaGetErrorString(ce__));                                               \
   } while (0)
 
-struct ScanResult;
 
 }  // namespace qcsim
 
@@ -54,7 +53,15 @@ struct qcsim_sv {
   double* d_scalars = nullptr;   // small result area
   qcsim::dd* d_chunk_sums = nullptr;
   uint64_t n_chunks = 0;
-  qcsim::ScanResult* d_scan = nullptr;
+  // measurement scan (reduce_kernels.cuh), allocated at the first measurement
+  double* d_prefix_hi = nullptr;          // [n_chunks] exact mass before the chunk (binade predictor)
+  unsigned long long* d_chunk_K = nullptr;  // [n_chunks] integer increments of the chunk
+  int* d_chunk_flags = nullptr;           // [n_chunks]
+  double* d_acc_start = nullptr;          // [n_chunks + 1] the reference's running sum at every chunk start
+  qcsim::dd* d_total = nullptr;           // exact mass of the slice (+ offset)
+  double* d_draws = nullptr;              // staging for draws / outcomes of a batch
+  unsigned long long* d_outcomes = nullptr;
+  uint64_t draws_capacity = 0;
   void* h_pinned = nullptr;      // 4 KiB pinned staging for scalar results
   qcsim::amp* d_qft_table = nullptr;  // per-pass item twiddle table of the QFT kernel (32 KiB)
 
@@ -105,6 +112,9 @@ int engine_permute_bits(qcsim_sv* h, const int* src_of);
 int engine_reverse_bits(qcsim_sv* h, int sq, int eq);
 int engine_qft_direct(qcsim_sv* h, int sq, int eq, bool do_swap, bool inverse);
 
+// outcomes[i] = first basis state whose running sum reaches probs[i] (the reference's sequential fp64 sum), or
+// ~0 when the draw is beyond the total; exact for every draw
+int engine_resolve_draws(qcsim_sv* h, const double* probs, uint64_t count, uint64_t* outcomes);
 int engine_pick_state(qcsim_sv* h, double prob, uint64_t fallback, uint64_t* outcome);
 int engine_sample(qcsim_sv* h, const double* probs, uint64_t count, uint64_t* outcomes);
 

@@ -2,16 +2,11 @@
 //
 // Replaces the reference's serial running sums (QubitRegister.h:169-195, 619-642;
 // QubitRegisterCalculator.h:948-1254).  The outcome of a measurement is defined there as the
-// first index i with  prob <= sum_{j<=i} |a_j|^2.  Here:
-//   1. k_chunk_sums   : every chunk of kChunk amplitudes -> its probability mass as an error-free
-//                       double-double (warp shuffle + shared-memory block reduction);
-//   2. k_find_chunk   : one block scans the chunk masses (double-double prefix) and locates the
-//                       chunk where the prefix first reaches prob;
-//   3. k_find_in_chunk: one block scans that chunk and returns the index.
-// |a|^2 is rounded exactly like the reference's -msse2 build (norm_rn), and the prefixes are
-// exact to ~2^-100, so the outcome equals the reference's unless prob lies within the rounding
-// error of the reference's own sequential fp64 sum (~sqrt(i) * 1e-16) of a bin edge.
-// Bound: HBM, 16 B per amplitude read once.
+// first index i with  prob <= acc_i,  acc_i = fl(acc_{i-1} + |a_i|^2)  in strictly sequential fp64.
+// The kernels below reproduce that running sum bit for bit, in parallel (see "the reference's
+// sequential running sum" further down); |a|^2 is rounded exactly like the reference's -msse2 build
+// (norm_rn).  Outcomes are therefore identical to the reference's for every draw.
+// Bound: HBM, 16 B per amplitude, read twice (chunk masses, chunk increments).
 #pragma once
 
 #include "common.cuh"
@@ -131,20 +126,27 @@ k_chunk_sums(const amp* __restrict__ psi, uint64_t n, uint64_t n_chunks, dd* __r
   }
 }
 
-struct ScanResult {
-  uint64_t chunk;    // chunk where the prefix first reaches prob (valid if found)
-  uint64_t index;    // local index of the outcome (valid if found, after k_find_in_chunk)
-  dd before;         // exact mass of everything before `chunk`, including `offset`
-  dd total;          // offset + exact mass of the whole local slice
-  double margin;     // min distance of prob to the two edges of the selected bin
-  int found;
-};
+// ---- the reference's sequential running sum, reproduced exactly and in parallel ----------------------
+// The reference measures with  acc_i = fl(acc_{i-1} + p_i),  p_i = |a_i|^2  (QubitRegister.h:172-190, 240-258,
+// 619-642; QubitRegisterCalculator.h:948-1254): a strictly sequential fp64 sum, and the outcome of a draw is the
+// first i with  prob <= acc_i.  A bit-identical outcome for EVERY draw needs the bit-identical acc_i -- an exact
+// (double-double) prefix is not enough when the draw lands within the rounding error of a bin edge, which at 30
+// qubits is most of the time.  The sum is nevertheless parallel: while acc stays inside one binade
+// [2^e, 2^(e+1)), it is an integer multiple of u = 2^(e-52) and  fl(acc + p) = acc + u * rint(p / u)  unless p/u
+// falls exactly on a half (round-half-even then depends on the running parity).  So
+//   1. k_chunk_sums        exact (double-double) mass per chunk of 4096 amplitudes -> the binade each chunk starts in
+//   2. k_chunk_increments  per chunk: K = sum rint(p_i / u) as an exact integer, flags for ties / overflow
+//   3. k_sequential_walk   ONE thread walks the chunks: acc += u K when the chunk stays inside its predicted binade
+//                          and had no tie, else it replays the chunk's 4096 additions one by one (a power-of-two
+//                          crossing happens at most ~once per binade, ties are rare): acc at every chunk start, exact
+//   4. k_resolve_draws     per draw: binary search over the chunk starts, then the reference's own loop inside one chunk.
+// Cost: two passes over the state + O(chunks) sequential work, for any number of draws.
+static constexpr unsigned long long kNoOutcome = ~0ULL;
 
-// Single block.  `offset` = exact mass owned by lower ranks (0 on one GPU).
+// exclusive prefix (hi word of the double-double) of the chunk masses, `offset` added: predicts the binade
 static __global__ void __launch_bounds__(1024)
-k_find_chunk(const dd* __restrict__ sums, uint64_t n_chunks, dd offset, double prob, ScanResult* __restrict__ res) {
+k_chunk_prefix(const dd* __restrict__ sums, uint64_t n_chunks, dd offset, double* __restrict__ prefix_hi, dd* __restrict__ total) {
   __shared__ dd tot[1024];
-  __shared__ unsigned long long first_chunk;
   const int t = threadIdx.x, T = blockDim.x;
   const uint64_t per = (n_chunks + T - 1) / T;
   const uint64_t lo = (uint64_t)t * per;
@@ -152,9 +154,7 @@ k_find_chunk(const dd* __restrict__ sums, uint64_t n_chunks, dd offset, double p
   dd acc = dd_make(0, 0);
   for (uint64_t c = lo; c < hi; ++c) acc = dd_add(acc, sums[c]);
   tot[t] = acc;
-  if (t == 0) first_chunk = ~0ULL;
   __syncthreads();
-  // exclusive prefix of the per-thread strips (serial over <= 1024 entries, one thread: cheap and exact-ordered)
   if (t == 0) {
     dd run = offset;
     for (int k = 0; k < T; ++k) {
@@ -162,135 +162,185 @@ k_find_chunk(const dd* __restrict__ sums, uint64_t n_chunks, dd offset, double p
       tot[k] = run;
       run = dd_add(run, v);
     }
-    res->total = run;
+    *total = run;
   }
   __syncthreads();
   dd run = tot[t];
   for (uint64_t c = lo; c < hi; ++c) {
-    const dd nxt = dd_add(run, sums[c]);
-    if (dd_reaches(prob, nxt)) {
-      atomicMin(&first_chunk, (unsigned long long)c);
-      break;
-    }
-    run = nxt;
-  }
-  __syncthreads();
-  // the winning strip re-derives the exact prefix before its chunk
-  if (first_chunk != ~0ULL && first_chunk >= lo && first_chunk < hi) {
-    dd r2 = tot[t];
-    for (uint64_t c = lo; c < first_chunk; ++c) r2 = dd_add(r2, sums[c]);
-    res->chunk = first_chunk;
-    res->before = r2;
-    res->found = 1;
-  }
-  if (t == 0 && first_chunk == ~0ULL) {
-    res->found = 0;
-    res->chunk = 0;
-    res->index = 0;
-    res->margin = 0;
+    prefix_hi[c] = run.hi;
+    run = dd_add(run, sums[c]);
   }
 }
 
-// Single block of kThreads: locate the outcome inside res->chunk.
-static __global__ void __launch_bounds__(kThreads)
-k_find_in_chunk(const amp* __restrict__ psi, uint64_t n, double prob, ScanResult* __restrict__ res) {
-  if (!res->found) return;
-  constexpr int PER = (int)(kChunk / kThreads);
-  __shared__ dd tot[kThreads];
-  __shared__ unsigned long long first_idx;
-  const uint64_t lo = res->chunk << kChunkLog2;
-  const int t = threadIdx.x;
-  double p[PER];
-  dd acc = dd_make(0, 0);
-#pragma unroll
-  for (int k = 0; k < PER; ++k) {
-    const uint64_t i = lo + (uint64_t)t * PER + k;
-    p[k] = (i < n) ? norm_rn(psi[i]) : 0.0;
-    acc = dd_add_d(acc, p[k]);
-  }
-  tot[t] = acc;
-  if (t == 0) first_idx = ~0ULL;
-  __syncthreads();
-  if (t == 0) {
-    dd run = res->before;
-    for (int k = 0; k < kThreads; ++k) {
-      const dd v = tot[k];
-      tot[k] = run;
-      run = dd_add(run, v);
-    }
-  }
-  __syncthreads();
-  dd run = tot[t];
-  int hit = -1;
-  dd prev = run, at = run;
-#pragma unroll
-  for (int k = 0; k < PER; ++k) {
-    const dd nxt = dd_add_d(run, p[k]);
-    if (hit < 0 && dd_reaches(prob, nxt)) {
-      hit = k;
-      prev = run;
-      at = nxt;
-    }
-    run = nxt;
-  }
-  if (hit >= 0) atomicMin(&first_idx, (unsigned long long)(lo + (uint64_t)t * PER + hit));
-  __syncthreads();
-  if (hit >= 0 && first_idx == lo + (uint64_t)t * PER + hit) {
-    res->index = first_idx;
-    const double up = (at.hi - prob) + at.lo;    // distance to the edge that was reached
-    const double dn = (prob - prev.hi) - prev.lo; // distance to the previous edge
-    res->margin = up < dn ? up : dn;
-  }
-  if (t == 0 && first_idx == ~0ULL) res->found = 0;  // cannot happen when k_find_chunk found it
-}
+// flag bits of a chunk
+constexpr int kChunkZero = 1;   // every |a|^2 of the chunk is 0: acc does not move
+constexpr int kChunkSlow = 2;   // tie, overflow, or no usable binade: replay one by one
 
-// Strict replay of the reference's sequential fp64 running sum (QubitRegister.h:172-190) over
-// local indices [0, upto]: acc_{i} = fl(acc_{i-1} + p_i), starting from `start`.  One block;
-// the adds are one dependent chain on a single thread, the loads are cooperative.
-// Writes the first index with prob <= acc (or ~0) and the final acc.
 static __global__ void __launch_bounds__(kThreads)
-k_sequential_scan(const amp* __restrict__ psi, uint64_t n, double start, double prob, unsigned long long* __restrict__ out_idx,
-                  double* __restrict__ out_acc) {
-  __shared__ double buf[2][kThreads * 8];
-  constexpr int TILE = kThreads * 8;
-  double acc = start;
-  unsigned long long found = ~0ULL;
-  const uint64_t n_tiles = (n + TILE - 1) / TILE;
-  // prefetch tile 0
-  for (int k = threadIdx.x; k < TILE; k += blockDim.x) {
-    const uint64_t i = k;
-    buf[0][k] = (i < n) ? norm_rn(psi[i]) : 0.0;
-  }
-  __syncthreads();
-  __shared__ int stop;
-  if (threadIdx.x == 0) stop = 0;
-  __syncthreads();
-  for (uint64_t tile = 0; tile < n_tiles && !stop; ++tile) {
-    const int cur = (int)(tile & 1);
-    if (threadIdx.x == 0) {
-      const uint64_t lo = tile * TILE;
-      const int lim = (int)((n - lo < (uint64_t)TILE) ? (n - lo) : (uint64_t)TILE);
-      for (int k = 0; k < lim; ++k) {
-        acc = __dadd_rn(acc, buf[cur][k]);
-        if (prob <= acc) {
-          found = lo + k;
-          stop = 1;
-          break;
+k_chunk_increments(const amp* __restrict__ psi, uint64_t n, uint64_t n_chunks, const double* __restrict__ prefix_hi,
+                   unsigned long long* __restrict__ K, int* __restrict__ flags) {
+  __shared__ unsigned long long shk[kThreads / 32];
+  __shared__ int shf[kThreads / 32];
+  for (uint64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+    const uint64_t lo = c << kChunkLog2;
+    const uint64_t hi = (lo + kChunk < n) ? lo + kChunk : n;
+    const double start = prefix_hi[c];
+    const int e = start > 0.0 ? ilogb(start) : -5000;
+    const bool usable = e > -900;           // p * 2^(52 - e) must not overflow; subnormal sums take the slow path
+    unsigned long long k = 0;
+    int slow = usable ? 0 : 1, nonzero = 0;
+    for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+      const double p = norm_rn(psi[i]);
+      if (p != 0.0) nonzero = 1;
+      if (usable) {
+        const double x = scalbn(p, 52 - e);  // exact: a power-of-two scale
+        if (!(x < 4503599627370496.0)) {     // >= 2^52: this element alone leaves the binade
+          slow = 1;
+        } else {
+          const double f = floor(x);
+          if (x - f == 0.5) slow = 1;        // round-half-even depends on the running parity
+          k += (unsigned long long)rint(x);
         }
       }
-    } else if (tile + 1 < n_tiles) {
-      const uint64_t lo = (tile + 1) * TILE;
-      for (int k = threadIdx.x - 1; k < TILE; k += blockDim.x - 1) {
-        const uint64_t i = lo + k;
-        buf[cur ^ 1][k] = (i < n) ? norm_rn(psi[i]) : 0.0;
+    }
+    // block reduction (exact integers; 4096 terms < 2^52 each cannot overflow 64 bits)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      k += __shfl_down_sync(0xffffffffu, k, o);
+      slow |= __shfl_down_sync(0xffffffffu, slow, o);
+      nonzero |= __shfl_down_sync(0xffffffffu, nonzero, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      shk[threadIdx.x >> 5] = k;
+      shf[threadIdx.x >> 5] = slow | (nonzero << 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long kk = 0;
+      int ff = 0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+        kk += shk[w];
+        ff |= shf[w];
       }
+      K[c] = kk;
+      flags[c] = ((ff & 2) ? 0 : kChunkZero) | ((ff & 1) ? kChunkSlow : 0);
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) {
-    *out_idx = found;
-    *out_acc = acc;
+}
+
+// One block; thread 0 carries the sum, the others stage chunk records.  acc_start[c] = the reference's running sum
+// before element c * 4096 (acc_start[n_chunks] = after the last element), starting from `start` (the sum the lower
+// ranks ended with on a sharded register).
+static __global__ void __launch_bounds__(kThreads)
+k_sequential_walk(const amp* __restrict__ psi, uint64_t n, uint64_t n_chunks, const double* __restrict__ prefix_hi,
+                  const unsigned long long* __restrict__ K, const int* __restrict__ flags, double start, double* __restrict__ acc_start,
+                  unsigned long long* __restrict__ n_slow_out) {
+  constexpr int TILE = 512;
+  __shared__ unsigned long long sK[TILE];
+  __shared__ int sF[TILE];
+  __shared__ int sE[TILE];
+  __shared__ double sOut[TILE];
+  __shared__ double sP[kChunk];
+  __shared__ double carry;
+  __shared__ int want_chunk;
+  unsigned long long n_slow = 0;
+  if (threadIdx.x == 0) carry = start;
+  __syncthreads();
+  for (uint64_t c0 = 0; c0 < n_chunks; c0 += TILE) {
+    const int cnt = (int)((n_chunks - c0 < (uint64_t)TILE) ? (n_chunks - c0) : (uint64_t)TILE);
+    for (int j = threadIdx.x; j < cnt; j += blockDim.x) {
+      sK[j] = K[c0 + j];
+      sF[j] = flags[c0 + j];
+      const double ph = prefix_hi[c0 + j];
+      sE[j] = ph > 0.0 ? ilogb(ph) : -5000;
+    }
+    __syncthreads();
+    int j = 0;
+    while (j < cnt) {  // uniform loop: thread 0 advances until it needs a chunk replayed
+      if (threadIdx.x == 0) {
+        double acc = carry;
+        int jj = j;
+        want_chunk = -1;
+        for (; jj < cnt; ++jj) {
+          sOut[jj] = acc;
+          const int f = sF[jj];
+          if (f & kChunkZero) continue;
+          bool fast = !(f & kChunkSlow) && acc > 0.0 && ilogb(acc) == sE[jj];
+          if (fast) {
+            const double nxt = acc + scalbn((double)sK[jj], sE[jj] - 52);  // exact while it stays inside the binade
+            if (ilogb(nxt) == sE[jj]) {
+              acc = nxt;
+              continue;
+            }
+          }
+          want_chunk = jj;  // replay this chunk element by element
+          break;
+        }
+        carry = acc;
+        if (want_chunk < 0) want_chunk = -1 - cnt;  // encoded: tile finished
+      }
+      __syncthreads();
+      const int w = want_chunk;
+      if (w < 0) {
+        j = cnt;
+        __syncthreads();
+        break;
+      }
+      // cooperative load of chunk w's probabilities, then thread 0 adds them in order
+      const uint64_t lo = (c0 + (uint64_t)w) << kChunkLog2;
+      for (int k2 = threadIdx.x; k2 < (int)kChunk; k2 += blockDim.x) {
+        const uint64_t i = lo + k2;
+        sP[k2] = (i < n) ? norm_rn(psi[i]) : 0.0;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double acc = carry;
+        for (int k2 = 0; k2 < (int)kChunk; ++k2) acc = __dadd_rn(acc, sP[k2]);
+        carry = acc;
+        ++n_slow;
+      }
+      j = w + 1;
+      __syncthreads();
+    }
+    for (int jj = threadIdx.x; jj < cnt; jj += blockDim.x) acc_start[c0 + jj] = sOut[jj];
+    __syncthreads();
   }
+  if (threadIdx.x == 0) {
+    acc_start[n_chunks] = carry;
+    if (n_slow_out) *n_slow_out = n_slow;
+  }
+}
+
+// One thread per draw.  outcome = first local index i with probs[d] <= acc_i, or kNoOutcome when the draw lies
+// outside (acc_start[0], acc_start[n_chunks]] (another rank's range, or beyond the total).
+static __global__ void __launch_bounds__(128)
+k_resolve_draws(const amp* __restrict__ psi, uint64_t n, uint64_t n_chunks, const double* __restrict__ acc_start,
+                const double* __restrict__ probs, uint64_t count, unsigned long long* __restrict__ outcomes) {
+  const uint64_t d = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= count) return;
+  const double prob = probs[d];
+  unsigned long long out = kNoOutcome;
+  if (prob > acc_start[0] && prob <= acc_start[n_chunks]) {
+    // last chunk c with acc_start[c] < prob (acc_start is non-decreasing): the hit is inside it
+    uint64_t lo = 0, hi = n_chunks;  // invariant: acc_start[lo] < prob <= acc_start[hi]
+    while (hi - lo > 1) {
+      const uint64_t mid = (lo + hi) >> 1;
+      if (acc_start[mid] < prob) lo = mid;
+      else hi = mid;
+    }
+    double acc = acc_start[lo];
+    const uint64_t b = lo << kChunkLog2;
+    const uint64_t e = (b + kChunk < n) ? b + kChunk : n;
+    for (uint64_t i = b; i < e; ++i) {
+      acc = __dadd_rn(acc, norm_rn(psi[i]));
+      if (prob <= acc) {
+        out = i;
+        break;
+      }
+    }
+  }
+  outcomes[d] = out;
 }
 
 }  // namespace qcsim

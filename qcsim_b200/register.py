@@ -166,12 +166,20 @@ class QubitRegister:
         res: Dict[int, int] = {}
         if nr == 0:
             return res
+        mask = None if first is None else ((1 << (second + 1)) - 1) - ((1 << first) - 1)
+        if nr == 1:
+            # the reference's single-shot shortcut (:231-236, 334-339): MeasureNoCollapse -- outcome 0 when the draw is beyond the
+            # total, no table cut; the range variant masks and shifts the ALREADY shifted outcome once more (:337)
+            if first is None:
+                meas = self.MeasureNoCollapse()
+            else:
+                meas = (self.MeasureNoCollapse(first, second) & mask) >> first
+            return {meas: 1}
         probs = np.array([self._draw() for _ in range(nr)], dtype=np.float64)
         outs = np.zeros(nr, dtype=np.uint64)
         _lib.check(self._lib.qcsim_sv_sample(self._h, probs.ctypes.data_as(C.c_void_p), nr,
                                              outs.ctypes.data_as(C.c_void_p)))
         if first is not None:
-            mask = ((1 << (second + 1)) - 1) - ((1 << first) - 1)
             outs = (outs & np.uint64(mask)) >> np.uint64(first)
         for v in outs.tolist():
             res[v] = res.get(v, 0) + 1

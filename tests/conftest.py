@@ -35,3 +35,24 @@ def have_ref():
 
     oracle.build_ref()
     return oracle.ref_available("sse2")
+
+
+@pytest.fixture(autouse=True)
+def _gpu_tests_check_against_the_reference_itself(request):
+    """Every `-m gpu` parity test compares with the compiled reference (oracle/_ref, kind == "reference"), never
+    silently with the C port: oracle.best_oracle raises under QCSIM_REQUIRE_REF when the reference build is missing."""
+    if request.node.get_closest_marker("gpu") is None:
+        yield
+        return
+    import oracle
+
+    assert oracle.ref_available("sse2"), "oracle/_ref/libqcsim_ref_sse2.so is missing: the GPU parity tests need the compiled reference"
+    old = os.environ.get("QCSIM_REQUIRE_REF")
+    os.environ["QCSIM_REQUIRE_REF"] = "1"
+    try:
+        yield
+    finally:
+        if old is None:
+            os.environ.pop("QCSIM_REQUIRE_REF", None)
+        else:
+            os.environ["QCSIM_REQUIRE_REF"] = old

@@ -104,6 +104,27 @@ def test_random_circuit_vs_oracle(n, layers):
         assert abs(gpu.norm2() - ref.norm2()) <= TOL
 
 
+def test_config2_full_depth_vs_reference():
+    """BASELINE config 2 at its stated DEPTH (200 layers; the generator is the one bench.py uses: 6800 gate applications
+    at 24 qubits, 8600 at 30) at 24 qubits, the largest size the compiled reference finishes in about a minute: amplitudes within 1e-12
+    and norm within 1e-12 of the reference, gate by gate and as fused blocks (whose 8x8 products are formed on the
+    host and applied with FMA, i.e. a different rounding order)."""
+    n, layers = 24, 200
+    circ = circuits.random_circuit(n, layers)
+    assert len(circ) == 34 * layers
+    with oracle.best_oracle(n) as ref:
+        assert ref.kind == "reference"
+        ref.apply_circuit(circ)
+        want, want_norm = ref.state(), ref.norm2()
+    for mode in ("unfused", "fused"):
+        with GpuSim(n, batch=(mode == "fused")) as gpu:
+            gpu.apply_circuit(circ)
+            d = maxdiff(gpu.state(), want)
+            assert d <= TOL, (mode, d)
+            assert abs(gpu.norm2() - want_norm) <= TOL, mode
+            print(f"\n[config 2, {n} q x {layers} layers, {mode}] max|d| = {d:.2e}, norm2 = {gpu.norm2():.15f} (reference {want_norm:.15f})")
+
+
 @pytest.mark.parametrize("n", [10, 20])
 def test_qft_iqft_config1(n):
     """BASELINE config 1: QFT then IQFT with MeasureAll, three start states."""
