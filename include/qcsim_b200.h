@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define QCSIM_ABI_VERSION 1
+#define QCSIM_ABI_VERSION 2
 
 /* error codes ------------------------------------------------------------------------------ */
 #define QCSIM_OK 0
@@ -128,9 +128,35 @@ int qcsim_sv_apply_batch(qcsim_sv* h, const qcsim_gate* gates, uint64_t count);
  * 1 = qcsim_sv_apply only queues; the queue is fused and flushed by the next call that
  *     observes the state (measure, download, norm, sync ...).  Results are identical to 1e-15. */
 int qcsim_sv_set_fusion(qcsim_sv* h, int enabled);
+/* ApplyOperatorMatrix (QubitRegister.h:499-505): psi = M psi for a dense 2^n x 2^n operator, ROW-major (re, im)
+ * pairs.  The reference's teaching path (Shor / dense-oracle Grover / phase estimation, and Compute / Uncompute of
+ * recorded gates on more than 3 qubits, :563,581): a device GEMV, registers of at most QCSIM_MAX_OPERATOR_QUBITS
+ * qubits (the matrix alone is 16 * 4^n bytes), unsharded. */
+#define QCSIM_MAX_OPERATOR_QUBITS 13
+int qcsim_sv_apply_operator(qcsim_sv* h, const double* m);
 /* QuantumFourierTransform::QFT / IQFT on qubits [sq, eq] (QuantumFourierTransform.h:35-87),
  * including QubitsSwapper::Swap when do_swap (QubitsSwapper.h:23-34) */
 int qcsim_sv_qft(qcsim_sv* h, uint64_t sq, uint64_t eq, int do_swap, int inverse);
+
+/* ---- circuit files ------------------------------------------------------------------------------
+ * A recorded gate stream (what ComputeStart/ComputeEnd record and ApplyGates / Compute replay, QubitRegister.h:493-497,
+ * 536-590) as a file both sides of the parity harness read: the engine through qcsim_sv_apply_circuit_file (=
+ * qcsim_sv_apply_batch on its records), the compiled reference through oracle/ref_driver.cpp::ref_apply_circuit_file.
+ * Layout (little endian): char magic[8] = "QCSIMC1\0"; uint32 n_qubits; uint32 reserved; uint64 count; then per gate
+ *   int32 nq, flags, gate_id, reserved; uint64 q, c1, c2; double params[4]; double m[2 * 4^nq] (row-major re, im).
+ * gate_id / params name the reference gate class (oracle/ref_driver.cpp: makeGate) or are -1 / 0 for a plain matrix;
+ * the engine only reads the matrix and the flags. */
+typedef struct qcsim_circuit_gate {
+  int32_t nq, flags, gate_id, reserved;
+  uint64_t q, c1, c2;
+  double params[4];
+  double m[128];
+} qcsim_circuit_gate;
+int qcsim_circuit_save(const char* path, uint32_t n_qubits, const qcsim_circuit_gate* gates, uint64_t count);
+/* *gates is malloc'ed by the library: release it with qcsim_circuit_free */
+int qcsim_circuit_load(const char* path, uint32_t* n_qubits, qcsim_circuit_gate** gates, uint64_t* count);
+void qcsim_circuit_free(qcsim_circuit_gate* gates);
+int qcsim_sv_apply_circuit_file(qcsim_sv* h, const char* path);
 
 /* ---- measurement (QubitRegister.h:169-224, 592-598, 619-642; Calculator :948-1254) --------- */
 /* `prob` is the reference's `1. - uniformZeroOne(rng)`; the RNG stays with the caller */
@@ -139,12 +165,13 @@ int qcsim_sv_measure(qcsim_sv* h, uint64_t first, uint64_t last, double prob, ui
 int qcsim_sv_measure_all_nocollapse(qcsim_sv* h, double prob, uint64_t* outcome);      /* MeasureNoCollapse() :619 */
 int qcsim_sv_measure_nocollapse(qcsim_sv* h, uint64_t first, uint64_t last, double prob, uint64_t* outcome); /* :705 */
 int qcsim_sv_qubit_probability(qcsim_sv* h, uint64_t q, double* p);                    /* GetQubitProbability :592 */
-/* RepeatedMeasure (QubitRegister.h:227-429): `count` draws against one cumulative table built
- * on the device; outcomes[i] is the full basis state for probs[i] */
+/* RepeatedMeasure (QubitRegister.h:227-429): `count` draws against ONE cumulative table -- the reference's sequential
+ * running sum, built once on the device (two passes over the state, whatever `count` is).  outcomes[i] is what the
+ * reference's std::lower_bound over its table gives for probs[i], including its quirks: the table is cut at the first
+ * entry above 1 - DBL_EPSILON (:250-254) and a draw above the last stored entry yields the table size (:268). */
 int qcsim_sv_sample(qcsim_sv* h, const double* probs, uint64_t count, uint64_t* outcomes);
-/* 0 (default): parallel scan with error-free (double-double) prefixes.
- * 1: additionally replays the reference's strictly sequential fp64 running sum around the
- *    selected edge so the outcome is bit-identical to the -msse2 CPU build for every draw. */
+/* Kept for ABI compatibility: every measurement reproduces the reference's strictly sequential fp64 running sum
+ * bit for bit (csrc/reduce_kernels.cuh), so there is no non-strict mode any more; the call is a no-op. */
 int qcsim_sv_set_strict_measure(qcsim_sv* h, int enabled);
 
 /* ---- introspection --------------------------------------------------------------------------- */

@@ -126,6 +126,8 @@ class RefOracle(_Base):
         L.ref_save_state.argtypes = [_VP]
         L.ref_restore_state.argtypes = [_VP, C.c_int]
         L.ref_apply_operator_matrix.argtypes = [_VP, _VP]
+        L.ref_apply_circuit_file.restype = C.c_long
+        L.ref_apply_circuit_file.argtypes = [_VP, C.c_char_p]
         self.L = L
         self.n = n
         self.dim = 1 << n
@@ -271,6 +273,13 @@ class RefOracle(_Base):
         m = np.ascontiguousarray(m, dtype=np.complex128)
         assert m.shape == (self.dim, self.dim)
         self._rc(self.L.ref_apply_operator_matrix(self.h, m.ctypes.data_as(_VP)))
+
+    def apply_circuit_file(self, path: str) -> int:
+        """replay a circuit file written by qcsim_b200.circuits.save_circuit; returns the number of gates applied"""
+        n = self.L.ref_apply_circuit_file(self.h, str(path).encode())
+        if n < 0:
+            self._rc(int(n))
+        return int(n)
 
     def grover_gates(self, n_search: int, marked: int) -> np.ndarray:
         nq = 2 * n_search - 1

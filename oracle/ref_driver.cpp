@@ -320,6 +320,49 @@ int ref_apply_operator_matrix(void* h, const double* m) {
   });
 }
 
+// Replay a circuit file (include/qcsim_b200.h "circuit files": the same file the engine replays through
+// qcsim_sv_apply_circuit_file).  Records that name a reference gate class (gate_id >= 0) are applied as that class,
+// with its virtual flags; the others as AppliedGate(matrix) -- the reference's ApplyGates path (QubitRegister.h:493-497).
+// Returns the number of gates applied, or < 0.
+long ref_apply_circuit_file(void* h, const char* path) {
+  RefRegister* r = static_cast<RefRegister*>(h);
+  long applied = -3;
+  const int rc = guarded([&] {
+    FILE* f = std::fopen(path, "rb");
+    if (!f) throw std::runtime_error(std::string("cannot open ") + path);
+    char magic[8];
+    uint32_t nq = 0, reserved = 0;
+    uint64_t count = 0;
+    bool ok = std::fread(magic, 1, 8, f) == 8 && std::memcmp(magic, "QCSIMC1\0", 8) == 0 && std::fread(&nq, 4, 1, f) == 1 &&
+              std::fread(&reserved, 4, 1, f) == 1 && std::fread(&count, 8, 1, f) == 1;
+    if (!ok || nq != r->getNrQubits()) {
+      std::fclose(f);
+      throw std::runtime_error("not a circuit file for this register");
+    }
+    for (uint64_t i = 0; i < count; ++i) {
+      int32_t head[4];
+      uint64_t q[3];
+      double params[4], m[128];
+      ok = std::fread(head, 4, 4, f) == 4 && head[0] >= 1 && head[0] <= 3 && std::fread(q, 8, 3, f) == 3 && std::fread(params, 8, 4, f) == 4;
+      const size_t nm = ok ? (size_t)2 << (2 * head[0]) : 0;
+      ok = ok && std::fread(m, 8, nm, f) == nm;
+      if (!ok) {
+        std::fclose(f);
+        throw std::runtime_error("truncated circuit file");
+      }
+      std::unique_ptr<Gate> g = head[2] >= 0 ? makeGate(head[2], params) : nullptr;
+      if (g) r->ApplyGate(*g, q[0], q[1], q[2]);
+      else {
+        QC::Gates::AppliedGate<Mat> ag(fromRowMajor(head[0], m), q[0], q[1], q[2]);
+        r->ApplyGate(ag);
+      }
+    }
+    std::fclose(f);
+    applied = (long)count;
+  });
+  return rc == 0 ? applied : rc;
+}
+
 // rng.seed(seed) then `count` draws of `1. - uniformZeroOne(rng)`: pins qcsim_b200/rng.py
 void ref_draws(void* h, uint64_t seed, int count, double* out) {
   RefRegister* r = static_cast<RefRegister*>(h);

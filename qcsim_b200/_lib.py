@@ -36,6 +36,13 @@ class GateStruct(C.Structure):
                 ("m", C.c_double * 128)]
 
 
+class CircuitGateStruct(C.Structure):
+    """struct qcsim_circuit_gate (one record of a circuit file)"""
+
+    _fields_ = [("nq", C.c_int32), ("flags", C.c_int32), ("gate_id", C.c_int32), ("reserved", C.c_int32), ("q", C.c_uint64),
+                ("c1", C.c_uint64), ("c2", C.c_uint64), ("params", C.c_double * 4), ("m", C.c_double * 128)]
+
+
 class Stats(C.Structure):
     """struct qcsim_stats"""
 
@@ -81,6 +88,11 @@ SIGNATURES = {
     "qcsim_sv_apply": (C.c_int, [_P, C.c_int, C.c_void_p, C.c_int, _U64, _U64, _U64]),
     "qcsim_sv_apply_batch": (C.c_int, [_P, C.c_void_p, _U64]),
     "qcsim_sv_set_fusion": (C.c_int, [_P, C.c_int]),
+    "qcsim_sv_apply_operator": (C.c_int, [_P, C.c_void_p]),
+    "qcsim_circuit_save": (C.c_int, [C.c_char_p, C.c_uint32, C.c_void_p, _U64]),
+    "qcsim_circuit_load": (C.c_int, [C.c_char_p, C.POINTER(C.c_uint32), C.POINTER(C.c_void_p), _U64P]),
+    "qcsim_circuit_free": (None, [C.c_void_p]),
+    "qcsim_sv_apply_circuit_file": (C.c_int, [_P, C.c_char_p]),
     "qcsim_sv_qft": (C.c_int, [_P, _U64, _U64, C.c_int, C.c_int]),
     "qcsim_sv_measure_all": (C.c_int, [_P, C.c_double, _U64P]),
     "qcsim_sv_measure": (C.c_int, [_P, _U64, _U64, C.c_double, _U64P]),

@@ -7,6 +7,8 @@ Randomness comes from a self-contained splitmix64 so circuits are bit-identical 
 from __future__ import annotations
 
 import math
+
+import numpy as np
 from typing import List, Tuple
 
 from . import gates
@@ -206,3 +208,48 @@ def grover_gates_circuit(n_search: int, marked: int, iterations: int = None, qub
 
         out = [relabel(*t) for t in out]
     return out
+
+
+# ---- circuit files (include/qcsim_b200.h "circuit files") ---------------------------------------------------
+def save_circuit(path: str, n: int, circuit: Circuit) -> None:
+    """Write `circuit` (a list of (gate, q, c1, c2)) for an n-qubit register as a circuit file: the form both the engine
+    (qcsim_sv_apply_circuit_file) and the compiled reference (oracle/ref_driver.cpp: ref_apply_circuit_file) replay."""
+    import ctypes as C
+
+    from . import _lib
+
+    lib = _lib.load()
+    arr = (_lib.CircuitGateStruct * max(len(circuit), 1))()
+    for i, (g, q, c1, c2) in enumerate(circuit):
+        r = arr[i]
+        r.nq, r.flags, r.gate_id, r.reserved, r.q, r.c1, r.c2 = g.nq, g.flags, g.gate_id, 0, q, c1, c2
+        for j, v in enumerate((list(g.params) + [0.0] * 4)[:4]):
+            r.params[j] = float(v)
+        flat = np.ascontiguousarray(g.matrix, dtype=np.complex128).view(np.float64).ravel()
+        C.memmove(r.m, flat.ctypes.data, flat.nbytes)
+    _lib.check(lib.qcsim_circuit_save(str(path).encode(), n, arr, len(circuit)))
+
+
+def load_circuit(path: str):
+    """-> (n_qubits, [(Gate, q, c1, c2)]) read back through the C ABI loader"""
+    import ctypes as C
+
+    from . import _lib
+    from .gates import Gate
+
+    lib = _lib.load()
+    n = C.c_uint32()
+    ptr = C.c_void_p()
+    count = C.c_uint64()
+    _lib.check(lib.qcsim_circuit_load(str(path).encode(), C.byref(n), C.byref(ptr), C.byref(count)))
+    out = []
+    try:
+        recs = C.cast(ptr, C.POINTER(_lib.CircuitGateStruct))
+        for i in range(count.value):
+            r = recs[i]
+            d = 1 << r.nq
+            m = np.frombuffer(r.m, dtype=np.complex128, count=d * d).reshape(d, d).copy()
+            out.append((Gate(f"file{i}", m, r.flags, r.gate_id, tuple(r.params)), int(r.q), int(r.c1), int(r.c2)))
+    finally:
+        lib.qcsim_circuit_free(ptr)
+    return n.value, out

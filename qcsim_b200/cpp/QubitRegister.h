@@ -316,11 +316,26 @@ namespace QC {
 				ApplyGate(gate);
 		}
 
-		// :499-505.  A dense 2^n x 2^n operator is O(4^n) memory: the teaching path of the reference,
-		// outside the accelerated hot path ("out of scope").
-		void ApplyOperatorMatrix(const MatrixClass& /*m*/)
+		// :499-505: registerStorage = m * registerStorage for a dense 2^n x 2^n operator -- a device GEMV, small registers
+		// only (QCSIM_MAX_OPERATOR_QUBITS); this is what Compute / Uncompute replay for recorded gates on more than
+		// three qubits (:563, 581) and what the dense-oracle algorithms (Shor, Grover, phase estimation) apply
+		void ApplyOperatorMatrix(const MatrixClass& m)
 		{
-			throw std::logic_error("qcsim_b200: ApplyOperatorMatrix (dense 2^n x 2^n operator) is not part of the accelerated path");
+			const size_t d = NrBasisStates;
+			if (static_cast<size_t>(m.rows()) != d || static_cast<size_t>(m.cols()) != d) throw std::invalid_argument("qcsim_b200: operator matrix must be 2^n x 2^n");
+			std::vector<double> rowMajor(2 * d * d);
+			for (size_t r = 0; r < d; ++r)
+				for (size_t c = 0; c < d; ++c)
+				{
+					const std::complex<double> z = m(r, c);  // Eigen is column-major; the ABI is row-major
+					rowMajor[2 * (r * d + c)] = z.real();
+					rowMajor[2 * (r * d + c) + 1] = z.imag();
+				}
+			Touch();
+			Check(qcsim_sv_apply_operator(handle, rowMajor.data()));
+
+			if (recordGates)
+				computeGates.emplace_back(Gates::AppliedGate<MatrixClass>(m));
 		}
 
 		const VectorClass& getRegisterStorage() const  // :507-510

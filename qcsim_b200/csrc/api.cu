@@ -232,6 +232,100 @@ int qcsim_sv_apply_batch(qcsim_sv* h, const qcsim_gate* gates, uint64_t count) {
   return QCSIM_OK;
 }
 
+int qcsim_sv_apply_operator(qcsim_sv* h, const double* m) {
+  API_GUARD(h);
+  if (!m) return fail(QCSIM_ERR_BAD_ARG, "null matrix");
+  if (h->world > 1) return fail(QCSIM_ERR_UNSUPPORTED, "ApplyOperatorMatrix is not supported on a sharded register");
+  if (h->n > QCSIM_MAX_OPERATOR_QUBITS)
+    return fail(QCSIM_ERR_UNSUPPORTED, "ApplyOperatorMatrix: a dense operator on %d qubits needs %.0f GiB; limit is %d qubits", h->n,
+                std::ldexp(16.0, 2 * h->n - 30), QCSIM_MAX_OPERATOR_QUBITS);
+  QCSIM_TRY(engine_flush(h));
+  h->stats.gates_applied++;
+  return engine_apply_operator(h, m);
+}
+
+/* ---- circuit files ---------------------------------------------------------------------------- */
+
+static const char kCircuitMagic[8] = {'Q', 'C', 'S', 'I', 'M', 'C', '1', '\0'};
+
+int qcsim_circuit_save(const char* path, uint32_t n_qubits, const qcsim_circuit_gate* gates, uint64_t count) {
+  if (!path || (!gates && count)) return fail(QCSIM_ERR_BAD_ARG, "null argument");
+  FILE* f = std::fopen(path, "wb");
+  if (!f) return fail(QCSIM_ERR_BAD_ARG, "cannot open %s for writing", path);
+  const uint32_t reserved = 0;
+  bool ok = std::fwrite(kCircuitMagic, 1, 8, f) == 8 && std::fwrite(&n_qubits, 4, 1, f) == 1 && std::fwrite(&reserved, 4, 1, f) == 1 &&
+            std::fwrite(&count, 8, 1, f) == 1;
+  for (uint64_t i = 0; ok && i < count; ++i) {
+    const qcsim_circuit_gate& g = gates[i];
+    if (g.nq < 1 || g.nq > 3) {
+      std::fclose(f);
+      return fail(QCSIM_ERR_BAD_ARG, "gate %llu acts on %d qubits", (unsigned long long)i, g.nq);
+    }
+    const size_t nm = (size_t)2 << (2 * g.nq);
+    ok = std::fwrite(&g.nq, 4, 4, f) == 4 && std::fwrite(&g.q, 8, 3, f) == 3 && std::fwrite(g.params, 8, 4, f) == 4 && std::fwrite(g.m, 8, nm, f) == nm;
+  }
+  ok = (std::fclose(f) == 0) && ok;
+  return ok ? QCSIM_OK : fail(QCSIM_ERR_BAD_ARG, "short write to %s", path);
+}
+
+int qcsim_circuit_load(const char* path, uint32_t* n_qubits, qcsim_circuit_gate** gates, uint64_t* count) {
+  if (!path || !gates || !count) return fail(QCSIM_ERR_BAD_ARG, "null argument");
+  *gates = nullptr;
+  *count = 0;
+  FILE* f = std::fopen(path, "rb");
+  if (!f) return fail(QCSIM_ERR_BAD_ARG, "cannot open %s", path);
+  char magic[8];
+  uint32_t nq = 0, reserved = 0;
+  uint64_t cnt = 0;
+  if (std::fread(magic, 1, 8, f) != 8 || std::memcmp(magic, kCircuitMagic, 8) != 0 || std::fread(&nq, 4, 1, f) != 1 || std::fread(&reserved, 4, 1, f) != 1 ||
+      std::fread(&cnt, 8, 1, f) != 1 || cnt > (1ULL << 32)) {
+    std::fclose(f);
+    return fail(QCSIM_ERR_BAD_ARG, "%s is not a qcsim circuit file", path);
+  }
+  qcsim_circuit_gate* out = static_cast<qcsim_circuit_gate*>(std::calloc(cnt ? cnt : 1, sizeof(qcsim_circuit_gate)));
+  if (!out) {
+    std::fclose(f);
+    return fail(QCSIM_ERR_OOM, "out of host memory for %llu gates", (unsigned long long)cnt);
+  }
+  for (uint64_t i = 0; i < cnt; ++i) {
+    qcsim_circuit_gate& g = out[i];
+    bool ok = std::fread(&g.nq, 4, 4, f) == 4 && g.nq >= 1 && g.nq <= 3 && std::fread(&g.q, 8, 3, f) == 3 && std::fread(g.params, 8, 4, f) == 4;
+    const size_t nm = ok ? (size_t)2 << (2 * g.nq) : 0;
+    ok = ok && std::fread(g.m, 8, nm, f) == nm;
+    if (!ok) {
+      std::free(out);
+      std::fclose(f);
+      return fail(QCSIM_ERR_BAD_ARG, "%s: truncated or corrupt at gate %llu", path, (unsigned long long)i);
+    }
+  }
+  std::fclose(f);
+  if (n_qubits) *n_qubits = nq;
+  *gates = out;
+  *count = cnt;
+  return QCSIM_OK;
+}
+
+void qcsim_circuit_free(qcsim_circuit_gate* gates) { std::free(gates); }
+
+int qcsim_sv_apply_circuit_file(qcsim_sv* h, const char* path) {
+  API_GUARD(h);
+  uint32_t nq = 0;
+  qcsim_circuit_gate* gates = nullptr;
+  uint64_t count = 0;
+  QCSIM_TRY(qcsim_circuit_load(path, &nq, &gates, &count));
+  int rc = QCSIM_OK;
+  if ((int)nq != h->n) rc = fail(QCSIM_ERR_BAD_ARG, "%s was recorded for %u qubits, the register has %d", path, nq, h->n);
+  for (uint64_t i = 0; rc == QCSIM_OK && i < count; ++i) rc = check_qubits(h, gates[i].nq, gates[i].q, gates[i].c1, gates[i].c2);
+  for (uint64_t i = 0; rc == QCSIM_OK && i < count; ++i) {
+    const qcsim_circuit_gate& g = gates[i];
+    h->stats.gates_applied++;
+    rc = engine_enqueue(h, classify(g.nq, g.m, g.flags, g.q, g.c1, g.c2));
+  }
+  qcsim_circuit_free(gates);
+  if (rc == QCSIM_OK && !h->fusion) rc = engine_flush(h);
+  return rc;
+}
+
 int qcsim_sv_set_fusion(qcsim_sv* h, int enabled) {
   API_GUARD(h);
   if (!enabled) QCSIM_TRY(engine_flush(h));

@@ -402,6 +402,47 @@ int engine_launch_local(qcsim_sv* h, const Op& op) {
   return fail(QCSIM_ERR_BAD_ARG, "unknown op kind");
 }
 
+// ---- dense operator (ApplyOperatorMatrix, QubitRegister.h:499-505): psi = M psi, small registers only ----------
+// one warp per row; the matrix (16 * 4^n bytes) is read once from a temporary device copy
+static __global__ void __launch_bounds__(kThreads) k_dense_operator(const amp* __restrict__ M, const amp* __restrict__ in, amp* __restrict__ out,
+                                                                    uint64_t dim) {
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t r = warp; r < dim; r += n_warps) {
+    amp acc = make_amp(0, 0);
+    const amp* row = M + r * dim;
+    for (uint64_t c = lane; c < dim; c += 32) acc = cadd(acc, cmul(row[c], in[c]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      acc.x += __shfl_down_sync(0xffffffffu, acc.x, o);
+      acc.y += __shfl_down_sync(0xffffffffu, acc.y, o);
+    }
+    if (lane == 0) out[r] = acc;
+  }
+}
+
+int engine_apply_operator(qcsim_sv* h, const double* m) {
+  const uint64_t dim = h->dim_local;
+  amp *dM = nullptr, *dout = nullptr;
+  cudaError_t ce = cudaMalloc(&dM, dim * dim * sizeof(amp));
+  if (ce == cudaSuccess) ce = cudaMalloc(&dout, dim * sizeof(amp));
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(dM, m, dim * dim * sizeof(amp), cudaMemcpyHostToDevice, h->stream);
+  if (ce == cudaSuccess) {
+    const uint64_t blocks = std::min<uint64_t>((dim * 32 + kThreads - 1) / kThreads, (uint64_t)kNumSMs * 8);
+    k_dense_operator<<<(unsigned)std::max<uint64_t>(blocks, 1), kThreads, 0, h->stream>>>(dM, h->psi, dout, dim);
+    ce = cudaGetLastError();
+  }
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(h->psi, dout, dim * sizeof(amp), cudaMemcpyDeviceToDevice, h->stream);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(h->stream);
+  cudaFree(dM);
+  cudaFree(dout);
+  if (ce != cudaSuccess)
+    return fail(ce == cudaErrorMemoryAllocation ? QCSIM_ERR_OOM : QCSIM_ERR_CUDA, "ApplyOperatorMatrix: %s", cudaGetErrorString(ce));
+  h->stats.kernel_launches += 1;
+  return QCSIM_OK;
+}
+
 int engine_apply_now(qcsim_sv* h, const Op& op) {
   if (h->world > 1) return dist_apply(h, op);
   return engine_launch_local(h, op);

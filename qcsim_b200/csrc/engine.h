@@ -101,6 +101,7 @@ int engine_save(qcsim_sv* h);
 int engine_restore(qcsim_sv* h, bool destructive);
 int engine_inner_product(qcsim_sv* a, qcsim_sv* b, double* re_im);
 
+int engine_apply_operator(qcsim_sv* h, const double* m_row_major);
 int engine_apply_now(qcsim_sv* h, const Op& op);
 int engine_enqueue(qcsim_sv* h, const Op& op);
 int engine_flush(qcsim_sv* h);

@@ -224,8 +224,18 @@ class QubitRegister:
                 self.computeGates.append((AppliedGate(g[0].matrix), g[1], g[2] if len(g) > 2 else 0, g[3] if len(g) > 3 else 0))
 
     def ApplyOperatorMatrix(self, m: np.ndarray) -> None:
-        raise NotImplementedError(
-            "dense 2^n x 2^n operators (QubitRegister.h:499-505) are outside the accelerated path")
+        """registerStorage = m * registerStorage (QubitRegister.h:499-505): dense 2^n x 2^n operator as a device GEMV;
+        small registers only (the engine refuses above QCSIM_MAX_OPERATOR_QUBITS = 13).  Recorded like the reference does."""
+        m = np.ascontiguousarray(m, dtype=np.complex128)
+        if m.shape != (self.NrBasisStates, self.NrBasisStates):
+            raise ValueError("operator matrix must be 2^n x 2^n")
+        _lib.check(self._lib.qcsim_sv_apply_operator(self._h, m.ctypes.data_as(C.c_void_p)))
+        if self.recordGates:
+            self.computeGates.append((AppliedGate(m), 0, 0, 0))
+
+    def ApplyCircuitFile(self, path: str) -> None:
+        """Replay a recorded gate stream from a circuit file (circuits.save_circuit; include/qcsim_b200.h "circuit files")."""
+        _lib.check(self._lib.qcsim_sv_apply_circuit_file(self._h, str(path).encode()))
 
     def QFT(self, sq: int = 0, eq: int = 2 ** 31 - 1, doSwap: bool = True, inverse: bool = False) -> None:
         """QuantumFourierTransform::QFT/IQFT as one engine call (QuantumFourierTransform.h:35-87)."""
@@ -272,14 +282,26 @@ class QubitRegister:
     def ComputeClear(self) -> None:
         self.computeGates = []
 
+    def _replay(self, recorded) -> None:
+        """QubitRegister.h:554-590: recorded gates on more than three qubits go through ApplyOperatorMatrix (:563, 581)"""
+        run = []
+        for g, q, c1, c2 in recorded:
+            if g.nq > 3:
+                self.ApplyGates(run)
+                run = []
+                self.ApplyOperatorMatrix(g.matrix)
+            else:
+                run.append((g, q, c1, c2))
+        self.ApplyGates(run)
+
     def Compute(self) -> None:
         save, self.recordGates = self.recordGates, False
-        self.ApplyGates(self.computeGates)
+        self._replay(self.computeGates)
         self.recordGates = save
 
     def Uncompute(self) -> None:
         save, self.recordGates = self.recordGates, False
-        self.ApplyGates([(g.adjoint(), q, c1, c2) for (g, q, c1, c2) in reversed(self.computeGates)])
+        self._replay([(g.adjoint(), q, c1, c2) for (g, q, c1, c2) in reversed(self.computeGates)])
         self.recordGates = save
 
     # -- save / restore / clone (QubitRegister.h:600-616, 662-674) ------------------------------------

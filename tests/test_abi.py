@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for name in names:
         assert hasattr(lib, name), f"{name} declared in include/qcsim_b200.h but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature in qcsim_b200/_lib.py"
-    assert lib.qcsim_abi_version() == 1
+    assert lib.qcsim_abi_version() == 2
 
 
 def test_product_fails_loudly_without_gpu():
