@@ -94,6 +94,13 @@ int qcsim_sv_create(qcsim_sv** out, int n_qubits, int device);
 int qcsim_nccl_unique_id(void* out_128_bytes);
 int qcsim_sv_create_sharded(qcsim_sv** out, int n_qubits, int device, int rank, int world,
                             const void* nccl_id_128_bytes);
+/* One host thread, several GPUs (the form QC::QubitRegister needs: one object, one caller): the register is sharded
+ * over `n_devices` (a power of two, <= 8) devices of this process on its top log2(n_devices) qubits.  Every call on
+ * the returned handle runs on all shards (one worker thread per device inside the library); global<->local qubit
+ * exchanges go through peer memory (cudaDeviceEnablePeerAccess), scalars through NCCL.  device_ids == NULL: devices
+ * 0 .. n_devices-1.  n_devices == 1 is qcsim_sv_create.  Not supported on such a handle: clone, device_ptr,
+ * apply_operator. */
+int qcsim_sv_create_multi(qcsim_sv** out, int n_qubits, int n_devices, const int* device_ids);
 int qcsim_sv_destroy(qcsim_sv* h);
 int qcsim_sv_clone(const qcsim_sv* src, qcsim_sv** out);
 int qcsim_sv_sync(qcsim_sv* h);  /* flush queued gates and wait for the stream */

@@ -67,6 +67,7 @@ SIGNATURES = {
     "qcsim_sv_create": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int]),
     "qcsim_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "qcsim_sv_create_sharded": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "qcsim_sv_create_multi": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.POINTER(C.c_int)]),
     "qcsim_sv_destroy": (C.c_int, [_P]),
     "qcsim_sv_clone": (C.c_int, [_P, C.POINTER(_P)]),
     "qcsim_sv_sync": (C.c_int, [_P]),

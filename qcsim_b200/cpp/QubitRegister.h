@@ -88,7 +88,7 @@ namespace QC {
 			: NrQubits(N), NrBasisStates(1ULL << NrQubits), uniformZeroOne(0, 1), recordGates(false)
 		{
 			assert(N > 0);
-			Check(qcsim_sv_create(&handle, static_cast<int>(N), DefaultDevice()));
+			CreateHandle(N);
 			SeedFromClock(addseed);
 		}
 
@@ -98,7 +98,7 @@ namespace QC {
 			: NrQubits(N), NrBasisStates(1ULL << NrQubits), uniformZeroOne(0, 1), recordGates(false)
 		{
 			assert(N > 0);
-			Check(qcsim_sv_create(&handle, static_cast<int>(N), DefaultDevice()));
+			CreateHandle(N);
 			if (static_cast<size_t>(v.size()) == NrBasisStates) Upload(v);
 			SeedFromClock(addseed);
 		}
@@ -366,8 +366,7 @@ namespace QC {
 		double stateFidelity(const VectorClass& state) const  // :527-534
 		{
 			if (NrBasisStates != static_cast<size_t>(state.size())) return 0;
-			qcsim_sv* other = nullptr;
-			Check(qcsim_sv_create(&other, static_cast<int>(NrQubits), DefaultDevice()));
+			qcsim_sv* other = NewHandle(NrQubits);  // same device(s) as this register
 			int rc = qcsim_sv_upload(other, reinterpret_cast<const double*>(&state(0)), 0, NrBasisStates);
 			double p[2] = { 0, 0 };
 			if (rc == QCSIM_OK) rc = qcsim_sv_inner_product(handle, other, p);  // conj(register) . state
@@ -559,6 +558,43 @@ namespace QC {
 		{
 			const char* s = std::getenv("QCSIM_B200_DEVICE");
 			return s ? std::atoi(s) : 0;
+		}
+
+		// QCSIM_B200_DEVICES=0,1,2,3 shards the register over those GPUs of this process (qcsim_sv_create_multi);
+		// registers too small to shard (fewer than 8 qubits per device) stay on the first device
+		void CreateHandle(size_t N)
+		{
+			handle = NewHandle(N);
+			// QCSIM_B200_FUSION=1: ApplyGate only queues; the queue runs as fused gate blocks when the state is observed
+			if (const char* f = std::getenv("QCSIM_B200_FUSION"))
+				if (std::atoi(f) != 0) Check(qcsim_sv_set_fusion(handle, 1));
+		}
+
+		static qcsim_sv* NewHandle(size_t N)
+		{
+			qcsim_sv* out = nullptr;
+			std::vector<int> ids;
+			if (const char* s = std::getenv("QCSIM_B200_DEVICES"))
+			{
+				std::string item;
+				for (const char* p = s;; ++p)
+				{
+					if (*p == ',' || *p == 0)
+					{
+						if (!item.empty()) ids.push_back(std::atoi(item.c_str()));
+						item.clear();
+						if (*p == 0) break;
+					}
+					else item.push_back(*p);
+				}
+			}
+			size_t log2w = 0;
+			while ((size_t(1) << (log2w + 1)) <= ids.size()) ++log2w;
+			if (ids.size() > 1 && N >= log2w + 8)
+				Check(qcsim_sv_create_multi(&out, static_cast<int>(N), 1 << log2w, ids.data()));
+			else
+				Check(qcsim_sv_create(&out, static_cast<int>(N), ids.empty() ? DefaultDevice() : ids[0]));
+			return out;
 		}
 
 		static size_t MeasuredMask(size_t firstQubit, size_t secondQubit)  // QubitRegisterCalculator.h:1128-1130

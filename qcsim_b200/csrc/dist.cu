@@ -12,6 +12,8 @@
 //                     on every rank.
 #include <nccl.h>
 
+#include <unistd.h>
+
 #include <algorithm>
 #include <chrono>
 #include <cstdlib>
@@ -57,6 +59,7 @@ struct DistState {
   // peer-memory path: every rank's slice mapped into this process through CUDA IPC
   bool p2p = false;
   amp* peer_psi[64] = {};
+  bool peer_is_ipc[64] = {};  // mapped through CUDA IPC (another process) -- same-process peers are plain pointers
   // SPMD discipline: every rank must make the same collective-bearing calls in the same order.
   // seq_hash folds (kind, arguments) of each such call; with QCSIM_SPMD_CHECK=1 the hashes are
   // compared across ranks before every collective and a mismatch is an error instead of a hang.
@@ -323,8 +326,9 @@ __global__ void __launch_bounds__(256) k_exchange_swap_v1(amp* __restrict__ mine
 static void close_peers(qcsim_sv* h) {
   DistState* d = st(h);
   for (int r = 0; r < h->world; ++r) {
-    if (d->peer_psi[r] && r != h->rank) cudaIpcCloseMemHandle(d->peer_psi[r]);
+    if (d->peer_psi[r] && r != h->rank && d->peer_is_ipc[r]) cudaIpcCloseMemHandle(d->peer_psi[r]);
     d->peer_psi[r] = nullptr;
+    d->peer_is_ipc[r] = false;
   }
   d->p2p = false;
 }
@@ -338,33 +342,59 @@ static int setup_peers(qcsim_sv* h) {
   const char* mode = std::getenv("QCSIM_EXCHANGE");
   const bool want = !(mode && std::strcmp(mode, "nccl") == 0);
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-  if (h->world * 8 + 8 > 200) return fail(QCSIM_ERR_BAD_ARG, "internal: too many ranks for the handle exchange");
-  cudaIpcMemHandle_t mine_h;
-  std::memset(&mine_h, 0, sizeof mine_h);
+  // per rank: 64-byte IPC handle | pid | raw device pointer | device ordinal  (11 doubles)
+  struct PeerRecord {
+    cudaIpcMemHandle_t ipc;
+    int64_t pid;
+    uint64_t ptr;
+    int64_t device;
+  };
+  static_assert(sizeof(PeerRecord) == 88, "peer record layout");
+  constexpr int kRec = sizeof(PeerRecord) / sizeof(double);
+  if (h->world * kRec > 200) return fail(QCSIM_ERR_BAD_ARG, "internal: too many ranks for the handle exchange");
+  PeerRecord mine;
+  std::memset(&mine, 0, sizeof mine);
+  mine.pid = (int64_t)getpid();
+  mine.ptr = (uint64_t)(uintptr_t)h->psi;
+  mine.device = h->device;
   double ok = want ? 1.0 : 0.0;
-  if (want && cudaIpcGetMemHandle(&mine_h, h->psi) != cudaSuccess) {
-    cudaGetLastError();
-    ok = 0.0;
+  if (want && cudaIpcGetMemHandle(&mine.ipc, h->psi) != cudaSuccess) {
+    cudaGetLastError();  // not fatal yet: same-process peers do not need the IPC handle
+    std::memset(&mine.ipc, 0, sizeof mine.ipc);
   }
-  double* slot_mine = d->d_small + 8 * h->rank;  // 64 bytes per rank
-  CUDA_TRY(cudaMemcpyAsync(slot_mine, &mine_h, 64, cudaMemcpyHostToDevice, h->stream));
-  NCCL_TRY(ncclAllGather(slot_mine, d->d_small, 8, ncclDouble, d->comm, h->stream));
-  cudaIpcMemHandle_t all[64];
-  CUDA_TRY(cudaMemcpyAsync(all, d->d_small, 64 * h->world, cudaMemcpyDeviceToHost, h->stream));
+  double* slot_mine = d->d_small + kRec * h->rank;
+  CUDA_TRY(cudaMemcpyAsync(slot_mine, &mine, sizeof mine, cudaMemcpyHostToDevice, h->stream));
+  NCCL_TRY(ncclAllGather(slot_mine, d->d_small, kRec, ncclDouble, d->comm, h->stream));
+  PeerRecord all[kMaxWorld];
+  CUDA_TRY(cudaMemcpyAsync(all, d->d_small, sizeof(PeerRecord) * h->world, cudaMemcpyDeviceToHost, h->stream));
   QCSIM_TRY(engine_wait(h));
   if (ok != 0.0) {
     for (int r = 0; r < h->world; ++r) {
+      d->peer_is_ipc[r] = false;
       if (r == h->rank) {
         d->peer_psi[r] = h->psi;
         continue;
       }
+      if (all[r].pid == mine.pid) {
+        // same process (qcsim_sv_create_multi: one worker thread per device): plain pointer + peer access
+        const cudaError_t ce = cudaDeviceEnablePeerAccess((int)all[r].device, 0);
+        if (ce != cudaSuccess && ce != cudaErrorPeerAccessAlreadyEnabled) {
+          cudaGetLastError();
+          ok = 0.0;
+          break;
+        }
+        cudaGetLastError();
+        d->peer_psi[r] = (amp*)(uintptr_t)all[r].ptr;
+        continue;
+      }
       void* ptr = nullptr;
-      if (cudaIpcOpenMemHandle(&ptr, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      if (cudaIpcOpenMemHandle(&ptr, all[r].ipc, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
         cudaGetLastError();
         ok = 0.0;
         break;
       }
       d->peer_psi[r] = (amp*)ptr;
+      d->peer_is_ipc[r] = true;
     }
   }
   double agree = ok;  // every rank must take the same path

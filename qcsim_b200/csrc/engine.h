@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <cstdarg>
 #include <cstdint>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -71,6 +72,7 @@ struct qcsim_sv {
 
   void* nccl_comm = nullptr;     // ncclComm_t when world > 1
   void* dist = nullptr;          // sharding state (dist.cu)
+  void* multi = nullptr;         // single-process multi-device front (multi.cu): this handle owns one shard per device
 
   qcsim_stats stats = {};
 };
@@ -84,6 +86,15 @@ int fusion_init_device_kernels();
 // never arrive (the ranks made different calls): the wait is bounded (QCSIM_COLLECTIVE_TIMEOUT_S,
 // default 300 s) and ends in QCSIM_ERR_NCCL instead of spinning.
 int engine_wait(qcsim_sv* h);
+// Single-process multi-GPU (qcsim_sv_create_multi): the front handle owns one sharded register per device, each
+// driven by its own worker thread; every API call is forwarded to all shards in lock step (multi.cu).
+int multi_create(qcsim_sv** out, int n_qubits, int n_devices, const int* device_ids);
+int multi_destroy(qcsim_sv* front);
+int multi_world(const qcsim_sv* front);
+qcsim_sv* multi_shard(const qcsim_sv* front, int rank);
+// runs fn(shard, rank) on every worker thread at once; returns the first failing rank's code (its message becomes
+// this thread's qcsim_last_error)
+int multi_forward(qcsim_sv* front, const std::function<int(qcsim_sv*, int)>& fn);
 int engine_create(qcsim_sv** out, int n_qubits, int device, int rank, int world, const void* nccl_id);
 int engine_nccl_unique_id(void* out128);
 int engine_destroy(qcsim_sv* h);

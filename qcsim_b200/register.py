@@ -31,7 +31,7 @@ class QubitRegister:
     OneQubitOmpLimit = 8192  # QubitRegisterCalculator.h:1276, kept for source compatibility
 
     def __init__(self, N: int = 3, addseed: int = 0, device: int = 0, *, seed: Optional[int] = None,
-                 _handle=None, max_host_qubits: int = 31):
+                 _handle=None, max_host_qubits: int = 31, devices: Optional[Sequence[int]] = None):
         assert N > 0
         self._lib = _lib.load()
         self.NrQubits = int(N)
@@ -39,7 +39,12 @@ class QubitRegister:
         self._max_host_qubits = max_host_qubits
         if _handle is None:
             h = C.c_void_p()
-            _lib.check(self._lib.qcsim_sv_create(C.byref(h), self.NrQubits, device))
+            if devices is not None and len(devices) > 1:
+                # one object, one caller, several GPUs of this process (qcsim_sv_create_multi)
+                ids = (C.c_int * len(devices))(*devices)
+                _lib.check(self._lib.qcsim_sv_create_multi(C.byref(h), self.NrQubits, len(devices), ids))
+            else:
+                _lib.check(self._lib.qcsim_sv_create(C.byref(h), self.NrQubits, devices[0] if devices else device))
             self._h = h
         else:
             self._h = _handle

@@ -38,6 +38,7 @@ class GroverProbe : public Grover::GroverAlgorithmWithGatesOracle<Vec, Mat> {
 public:
   explicit GroverProbe(size_t n) : Grover::GroverAlgorithmWithGatesOracle<Vec, Mat>(n, 12345u) {}
   void run() { ExecuteWithoutMeasurement(); }
+  auto& R() { return reg; }  // the drop-in register inside the reference algorithm (QuantumAlgorithm.h:204)
 };
 class DraperProbe : public Adders::DraperAdder<Vec, Mat> {
 public:
@@ -95,6 +96,23 @@ int main(int argc, char** argv) {
       g.run();
       append_state(argv[4], g.getRegisterStorage());
       std::printf("qubits %zu\n", g.getNrQubits());
+    } else if (mode == "grover_ranges") {  // grover_ranges n_search marked out.bin : 16 sampled ranges of 4096 amplitudes + P(marked)
+      const size_t ns = std::stoul(argv[2]), marked = std::stoul(argv[3]);
+      GroverProbe g(ns);
+      g.setCorrectQuestionState(marked);
+      g.run();
+      const size_t nq = g.getNrQubits(), dim = size_t(1) << nq, cnt = 4096;
+      Vec buf(cnt);
+      for (size_t j = 0; j < 16; ++j) {
+        const size_t first = ((dim / 16) * j + 4096 * j) & ~size_t(4095);
+        g.R().DownloadRange(&buf(0), first < dim - cnt ? first : dim - cnt, cnt);
+        append_state(argv[4], buf);
+      }
+      std::printf("qubits %zu\n", nq);
+      std::printf("norm2 %.17g\n", g.R().Norm2());
+      // every search qubit (the low ns bits) reads its bit of the marked string with probability ~1 after the
+      // reference's round(pi/4 sqrt(2^ns)) iterations
+      for (size_t q = 0; q < ns; ++q) std::printf("pq %zu %.17g\n", q, g.R().GetQubitProbability(q));
     } else if (mode == "draper") {  // draper n_bits n1 n2 out.bin
       const size_t nb = std::stoul(argv[2]), n1 = std::stoul(argv[3]), n2 = std::stoul(argv[4]);
       DraperProbe a(nb);
