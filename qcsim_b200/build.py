@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libqcsim_b200.so")
 
-SOURCES = ["api.cu", "engine.cu", "fusion.cu", "dist.cu", "multi.cu"]
+SOURCES = ["api.cu", "engine.cu", "fusion.cu", "dist.cu", "multi.cu", "qft_pipe.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -454,6 +454,7 @@ static void harvest_timings(qcsim_sv* h, bool wait) {
 static int do_exchange_nccl_top(qcsim_sv* h, const DistStep& ex);
 
 static int do_exchange(qcsim_sv* h, const DistStep& ex) {
+  NvtxRange nvtx_range("qcsim.exchange");
   DistState* d = st(h);
   const int k = ex.k, nl = h->n_local;
   if (k < 1 || k > kMaxExchange) return fail(QCSIM_ERR_BAD_ARG, "internal: bad exchange width");
@@ -624,6 +625,7 @@ int dist_apply(qcsim_sv* h, const Op& op) {
 }
 
 int dist_canonicalize(qcsim_sv* h) {
+  NvtxRange nvtx_range("qcsim.canonicalize_layout");
   DistState* d = st(h);
   if (d->layout.is_identity()) return QCSIM_OK;
   return run_steps(h, dist_plan_canonicalize(d->layout));

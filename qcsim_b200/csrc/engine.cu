@@ -224,6 +224,7 @@ int engine_transfer(qcsim_sv* h, double* host, uint64_t first, uint64_t count, b
 }
 
 int engine_masked_norm2(qcsim_sv* h, uint64_t mask, uint64_t want, double* out) {
+  NvtxRange nvtx_range("qcsim.probability_reduction");
   // logical (mask, want) -> physical bit positions of the current layout
   uint64_t pmask = mask, pwant = want;
   if (h->world > 1) dist_map_mask(h, mask, want, &pmask, &pwant);
@@ -251,6 +252,7 @@ int engine_scale(qcsim_sv* h, double f) {
 }
 
 int engine_collapse(qcsim_sv* h, uint64_t mask, uint64_t want, double f) {
+  NvtxRange nvtx_range("qcsim.collapse");
   uint64_t pmask = mask, pwant = want;
   if (h->world > 1) dist_map_mask(h, mask, want, &pmask, &pwant);
   const uint64_t base = (uint64_t)h->rank << h->n_local;
@@ -520,13 +522,38 @@ static void item_bit_order(int k, uint32_t reg_mask, uint32_t* words, int n_word
 // every lower qubit down to r_floor, wherever it lives: local bits, or rank bits on a sharded register).
 // phys_of maps logical qubits to physical index bits (nullptr: identity); the qubits [lo, hi] must sit on local
 // positions, in any order.
+static int engine_qft_passes_plain(qcsim_sv* h, int lo, int hi, bool inverse, int r_floor, const int* phys_of);
+
 int engine_qft_passes(qcsim_sv* h, int lo, int hi, bool inverse, int r_floor, const int* phys_of) {
-  const int nl = h->n_local;
   int ident[64];
   if (!phys_of) {
     for (int q = 0; q < 64; ++q) ident[q] = q;
     phys_of = ident;
   }
+  static const bool plain_only = std::getenv("QCSIM_QFT_PLAIN") != nullptr;
+  if (plain_only || !fusion_pipe_available() || h->n_local < 11) return engine_qft_passes_plain(h, lo, hi, inverse, r_floor, phys_of);
+  // TMA-staged passes (qft_pipe.cu): contiguous slices of the targets, as many qubits per pass as fit an 11-bit tile
+  // next to qubits 0..2; top-down for the QFT, bottom-up for the IQFT
+  int cur = inverse ? lo : hi;
+  while (inverse ? cur <= hi : cur >= lo) {
+    int phys[16], left = inverse ? hi - cur + 1 : cur - lo + 1;
+    const int look = std::min(left, 11);
+    for (int j = 0; j < look; ++j) phys[j] = phys_of[inverse ? cur + j : cur - j];
+    for (int j = 0; j < look; ++j)
+      if (phys[j] < 0 || phys[j] >= h->n_local) return fail(QCSIM_ERR_BAD_ARG, "internal: QFT target qubit is not on a local position");
+    const int n = qft_pipe_pass_capacity(phys, look);
+    const int a = inverse ? cur : cur - n + 1, b = inverse ? cur + n - 1 : cur;
+    const int rc = qft_pipe_pass(h, a, b, inverse, r_floor, phys_of);
+    if (rc == QCSIM_ERR_UNSUPPORTED) QCSIM_TRY(engine_qft_passes_plain(h, a, b, inverse, r_floor, phys_of));
+    else QCSIM_TRY(rc);
+    cur = inverse ? b + 1 : a - 1;
+  }
+  return QCSIM_OK;
+}
+
+// the same with plain tile passes (k_qft_pass: 12-bit tiles staged by the CTA itself): small registers, fallback
+static int engine_qft_passes_plain(qcsim_sv* h, int lo, int hi, bool inverse, int r_floor, const int* phys_of) {
+  const int nl = h->n_local;
   struct Grp { int top, size; };
   std::vector<Grp> groups;  // top-down
   for (int top = hi; top >= lo;) {
@@ -603,12 +630,14 @@ int engine_qft_passes(qcsim_sv* h, int lo, int hi, bool inverse, int r_floor, co
     }
     const size_t smem = (sizeof(amp) << k) + sizeof(amp) * kMaxQftGroups;
     const uint64_t grid = std::min<uint64_t>(A.n_tiles, (uint64_t)kNumSMs * 3);
-    if (!h->d_qft_table) CUDA_TRY(cudaMalloc(&h->d_qft_table, sizeof(amp) * kMaxQftGroups * kQftItemsMax));
+    // twiddle table (16 B per item) followed by the slot table (4 B per item)
+    if (!h->d_qft_table) CUDA_TRY(cudaMalloc(&h->d_qft_table, (sizeof(amp) + sizeof(uint32_t)) * kMaxQftGroups * kQftItemsMax));
+    uint32_t* const d_slots = reinterpret_cast<uint32_t*>(h->d_qft_table + kMaxQftGroups * kQftItemsMax);
     if (k == 12) {
-      k_qft_item_table<<<kMaxQftGroups * kQftItemsMax / 256, 256, 0, h->stream>>>(h->d_qft_table, A);
+      k_qft_item_table<<<kMaxQftGroups * kQftItemsMax / 256, 256, 0, h->stream>>>(h->d_qft_table, d_slots, A);
       h->stats.kernel_launches += 1;
     }
-    k_qft_pass<<<(unsigned)grid, kTileThreads, smem, h->stream>>>(h->psi, h->d_qft_table, A);
+    k_qft_pass<<<(unsigned)grid, kTileThreads, smem, h->stream>>>(h->psi, h->d_qft_table, d_slots, A);
     CUDA_TRY(cudaGetLastError());
     count_pass(h, h->dim_local);
     h->stats.fused_rounds += p.groups.size();
@@ -776,6 +805,7 @@ int engine_qft(qcsim_sv* h, uint64_t sq_, uint64_t eq_, bool do_swap, bool inver
 
 // the transform itself, on qubits [sq, eq] (already validated, nothing queued before it)
 int engine_qft_direct(qcsim_sv* h, int sq, int eq, bool do_swap, bool inverse) {
+  NvtxRange nvtx_range("qcsim.qft");
   if (h->world > 1) {
     int handled = 0;
     QCSIM_TRY(dist_qft(h, sq, eq, do_swap, inverse, &handled));
@@ -815,6 +845,7 @@ static int ensure_scan_buffers(qcsim_sv* h, uint64_t count) {
 // The reference's running sum at every chunk start of this slice (reduce_kernels.cuh), then every draw resolved
 // against it.  On a sharded register the slices are chained: rank r starts from the sum rank r-1 ended with.
 int engine_resolve_draws(qcsim_sv* h, const double* probs, uint64_t count, uint64_t* outcomes) {
+  NvtxRange nvtx_range("qcsim.measure_scan");
   if (count == 0) return QCSIM_OK;
   QCSIM_TRY(engine_canonicalize(h));
   QCSIM_TRY(ensure_scan_buffers(h, count));

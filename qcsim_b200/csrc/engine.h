@@ -12,7 +12,17 @@
 #include "classify.h"
 #include "common.cuh"
 
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: named ranges for nsys / ncu timelines
+
 namespace qcsim {
+
+// RAII NVTX range around an engine phase: qcsim.fused_block, qcsim.qft, qcsim.measure, qcsim.exchange ...
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 extern thread_local std::string g_last_error;
 int fail(int code, const char* fmt, ...);

@@ -40,6 +40,7 @@ static_assert(kPipeSmemBytes <= 227 * 1024, "shared memory per CTA");
 int fusion_init_device_kernels() {  // per device, from engine_create
   CUDA_TRY(cudaFuncSetAttribute(k_tile_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (128 + 28) * 1024));
   CUDA_TRY(cudaFuncSetAttribute(k_tile_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmemBytes));
+  QCSIM_TRY(qft_pipe_init_device_kernels());
   return QCSIM_OK;
 }
 
@@ -55,13 +56,50 @@ static PFN_cuTensorMapEncodeTiled tensor_map_encoder() {
   return fn;
 }
 
+bool fusion_pipe_available() {
+  static const int legacy = env_int("QCSIM_TILE_LEGACY", 0);
+  return !legacy && tensor_map_encoder() != nullptr;
+}
+
+// Tensor map + coordinate recipe of a tile set (tile_pipe.cuh: PipeGeom) for the handle's state buffer.
+int fusion_fill_pipe_geom(qcsim_sv* h, const std::vector<int>& tile_sorted, const TmaTileGeom& g, PipeGeom* G) {
+  PFN_cuTensorMapEncodeTiled encode = tensor_map_encoder();
+  if (!encode) return QCSIM_ERR_UNSUPPORTED;
+  const int k = kPipeTileBits;
+  cuuint64_t gdim[5], gstride[4];
+  cuuint32_t box[5], estride[5] = {1, 1, 1, 1, 1};
+  gdim[0] = 16;  // doubles: 8 amplitudes
+  box[0] = 16;
+  for (int d = 1; d < 5; ++d) {
+    gdim[d] = 1ULL << g.dim_bits[d];
+    box[d] = 1u << g.box_bits[d];
+    gstride[d - 1] = (cuuint64_t)sizeof(amp) << g.dim_lo[d];  // bytes between consecutive coordinates of dim d
+  }
+  const CUresult cr = encode(&G->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, h->psi, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) return fail(QCSIM_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
+  G->n_tiles = 1ULL << (h->n_local - k);
+  G->n_enum = g.n_enum;
+  G->box_bytes = (int)(sizeof(amp) << g.box_log2);
+  for (int d = 0; d < 5; ++d) {
+    G->dim_lo[d] = g.dim_lo[d];
+    G->dim_mask_bits[d] = g.dim_bits[d];
+  }
+  for (int j = 0; j < 9; ++j) G->enum_pos[j] = j < g.n_enum ? g.enum_pos[j] : 0;
+  for (int j = 0; j < k; ++j) {
+    G->sorted_pos[j] = tile_sorted[j];
+    G->slot_pos[j] = g.slot_qubit[j];
+  }
+  G->pad = 0;
+  return QCSIM_OK;
+}
+
 // The TMA-staged, warp-specialised pass (tile_pipe.cuh).  Returns QCSIM_ERR_UNSUPPORTED when the tile
 // set has no TMA geometry (small registers), in which case the caller uses k_tile_pass.
 static int launch_pass_pipe(qcsim_sv* h, const std::vector<Op>& all, const PassPlan& plan_in) {
   TmaTileGeom g;
   if ((int)plan_in.tile.size() != kPipeTileBits || !tma_tile_geometry(plan_in.tile, h->n_local, &g)) return QCSIM_ERR_UNSUPPORTED;
-  PFN_cuTensorMapEncodeTiled encode = tensor_map_encoder();
-  if (!encode) return QCSIM_ERR_UNSUPPORTED;
+  if (!tensor_map_encoder()) return QCSIM_ERR_UNSUPPORTED;
   const int k = kPipeTileBits;
   // the tile in shared-memory slot order: everything downstream (round bits, item bits, variants) is in slot bits
   PassPlan plan = plan_in;
@@ -72,33 +110,8 @@ static int launch_pass_pipe(qcsim_sv* h, const std::vector<Op>& all, const PassP
   const std::vector<RoundPlan> rplan = schedule_rounds(all, plan, kMaxVariantBits, /*swizzle_kind=*/2);
 
   static thread_local PipePassArgs A;  // ~30 KiB: keep it off the stack; the launch copies it
-  {
-    cuuint64_t gdim[5], gstride[4];
-    cuuint32_t box[5], estride[5] = {1, 1, 1, 1, 1};
-    gdim[0] = 16;  // doubles: 8 amplitudes
-    box[0] = 16;
-    for (int d = 1; d < 5; ++d) {
-      gdim[d] = 1ULL << g.dim_bits[d];
-      box[d] = 1u << g.box_bits[d];
-      gstride[d - 1] = (cuuint64_t)sizeof(amp) << g.dim_lo[d];  // bytes between consecutive coordinates of dim d
-    }
-    const CUresult cr = encode(&A.tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, h->psi, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (cr != CUDA_SUCCESS) return fail(QCSIM_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
-  }
-  A.n_tiles = 1ULL << (h->n_local - k);
-  A.n_enum = g.n_enum;
-  A.box_bytes = (int)(sizeof(amp) << g.box_log2);
-  for (int d = 0; d < 5; ++d) {
-    A.dim_lo[d] = g.dim_lo[d];
-    A.dim_mask_bits[d] = g.dim_bits[d];
-  }
-  for (int j = 0; j < 9; ++j) A.enum_pos[j] = j < g.n_enum ? g.enum_pos[j] : 0;
-  for (int j = 0; j < k; ++j) {
-    A.sorted_pos[j] = plan_in.tile[j];
-    A.slot_pos[j] = g.slot_qubit[j];
-  }
-  const uint64_t grid = std::min<uint64_t>(A.n_tiles, (uint64_t)kNumSMs);
+  QCSIM_TRY(fusion_fill_pipe_geom(h, plan_in.tile, g, &A.geom));
+  const uint64_t grid = std::min<uint64_t>(A.geom.n_tiles, (uint64_t)kNumSMs);
   static const int debug = env_int("QCSIM_DEBUG_PLAN", 0);
 
   size_t r = 0;
@@ -239,6 +252,7 @@ int fusion_execute_partial(qcsim_sv* h, const std::vector<Op>& ops_in, std::vect
 
 // All qubit indices in `ops` are physical bit positions of the local slice.
 int fusion_execute_local(qcsim_sv* h, const std::vector<Op>& ops) {
+  NvtxRange nvtx_range("qcsim.gate_blocks");
   const int nl = h->n_local;
   const int N = (int)ops.size();
   static const int K_env = env_int("QCSIM_TILE_BITS", kMaxTileBits);

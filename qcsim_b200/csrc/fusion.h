@@ -22,4 +22,15 @@ int dist_execute(qcsim_sv* h, const std::vector<Op>& ops);
 
 int engine_launch_local(qcsim_sv* h, const Op& op);
 
+// TMA tile geometry of a tile set -> tensor map + coordinate recipe for the handle's state (fusion.cu)
+struct TmaTileGeom;
+struct PipeGeom;
+int fusion_fill_pipe_geom(qcsim_sv* h, const std::vector<int>& tile_sorted, const TmaTileGeom& g, PipeGeom* G);
+bool fusion_pipe_available();
+
+// QFT passes on the TMA pipeline (qft_pipe.cu)
+int qft_pipe_init_device_kernels();
+int qft_pipe_pass_capacity(const int* phys, int count);
+int qft_pipe_pass(qcsim_sv* h, int lo, int hi, bool inverse, int r_floor, const int* phys_of);
+
 }  // namespace qcsim

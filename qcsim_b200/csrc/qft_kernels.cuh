@@ -58,8 +58,8 @@ __device__ __forceinline__ void hadamard_pair(amp& a, amp& b, double s) {
   b = make_amp(s * (x.x - y.x), s * (x.y - y.y));
 }
 
-template <int G>
-__device__ __forceinline__ void qft_group(amp (&v)[8], const QftPassArgs& A, bool inverse, amp P) {
+template <int G, class Args>
+__device__ __forceinline__ void qft_group(amp (&v)[8], const Args& A, bool inverse, amp P) {
   constexpr int N = 1 << G;
   // amp x gets P^rev(x) = prod over set bits b of x of P^(2^(G-1-b)): the top register bit takes P,
   // the next one P^2, the lowest P^4 -- one power of P live at a time (register pressure)
@@ -124,7 +124,8 @@ __device__ __forceinline__ void qft_group(amp (&v)[8], const QftPassArgs& A, boo
 // three CTAs per SM.
 constexpr int kQftItemsMax = 2048;  // items of a 1-qubit group in a 12-bit tile (512 for a 3-qubit group)
 
-__device__ __forceinline__ uint64_t qft_logical(const QftPassArgs& A, uint64_t phys) {
+template <class Args>
+__device__ __forceinline__ uint64_t qft_logical(const Args& A, uint64_t phys) {
   uint64_t logical = 0;
 #pragma unroll 1
   for (int p = 0; p < A.n_phys; ++p) logical |= ((phys >> p) & 1ULL) << A.log_of[p];
@@ -139,7 +140,8 @@ __device__ __forceinline__ uint32_t qft_lbase(const QftGroup& grp, uint32_t item
 }
 
 // twiddle base exp(+-i pi R / 2^top) for the lower-qubit value R (masked to [sq, c0))
-__device__ __forceinline__ amp qft_base(const QftPassArgs& A, const QftGroup& grp, uint64_t logical, bool inverse) {
+template <class Args, class Group>
+__device__ __forceinline__ amp qft_base(const Args& A, const Group& grp, uint64_t logical, bool inverse) {
   const int c0 = grp.top_qubit - grp.size + 1;
   const uint64_t r_mask = ((1ULL << c0) - 1ULL) & ~((1ULL << A.sq) - 1ULL);
   const uint64_t R = logical & r_mask;
@@ -156,8 +158,10 @@ __device__ __forceinline__ uint64_t qft_phys_of_local(const QftPassArgs& A, uint
   return phys;
 }
 
-// table[g * kQftItemsMax + item] = thread part of the twiddle base of item `item` of group g (12-bit tiles)
-static __global__ void k_qft_item_table(amp* __restrict__ table, const __grid_constant__ QftPassArgs A) {
+// table[g * kQftItemsMax + item] = thread part of the twiddle base of item `item` of group g (12-bit tiles);
+// slots[same index] = swizzled shared-memory slot of the item's first amplitude (the 11-step bit deposit of
+// qft_lbase, done once per pass instead of once per item per tile)
+static __global__ void k_qft_item_table(amp* __restrict__ table, uint32_t* __restrict__ slots, const __grid_constant__ QftPassArgs A) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const int gi = i / kQftItemsMax;
   if (gi >= A.n_groups) return;
@@ -166,9 +170,11 @@ static __global__ void k_qft_item_table(amp* __restrict__ table, const __grid_co
   if (item >= (1u << (A.k - grp.size))) return;
   const uint32_t lbase = qft_lbase(grp, item);
   table[i] = qft_base(A, grp, qft_logical(A, qft_phys_of_local(A, lbase)), A.inverse != 0);
+  slots[i] = swz(lbase);
 }
 
 static __global__ void __launch_bounds__(kTileThreads, 3) k_qft_pass(amp* __restrict__ psi, const amp* __restrict__ tw_item,
+                                                                      const uint32_t* __restrict__ slot_item,
                                                                       const __grid_constant__ QftPassArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   amp* tile = reinterpret_cast<amp*>(smem_raw);
@@ -197,23 +203,33 @@ static __global__ void __launch_bounds__(kTileThreads, 3) k_qft_pass(amp* __rest
     if (tid < (uint32_t)A.n_groups) tw_cta[tid] = qft_base(A, A.groups[tid], qft_logical(A, gbase | A.rank_bits), inverse);
 
     if (mover) {
+      if (n_it == 8) {
+        // 12-bit tile: all eight 32-byte loads of the thread in flight at once, straight-line (a partially
+        // predicated register array ended up in local memory: the load phase was a third of the kernel)
+        const uint64_t g9 = 1ULL << A.tpos[9], g10 = 1ULL << A.tpos[10], g11 = 1ULL << A.tpos[11];
+        const amp* src = psi + (gbase | g_fixed);
+        const amp2 x0 = ld_amp2(src), x1 = ld_amp2(src + g9), x2 = ld_amp2(src + g10), x3 = ld_amp2(src + (g9 | g10));
+        const amp2 x4 = ld_amp2(src + g11), x5 = ld_amp2(src + (g11 | g9)), x6 = ld_amp2(src + (g11 | g10)), x7 = ld_amp2(src + (g11 | g10 | g9));
+#define QCSIM_QFT_PUT(U, X)                           \
+  {                                                   \
+    const uint32_t s_ = s_fixed ^ swz((uint32_t)(U) << 9); \
+    tile[s_] = (X).a;                                 \
+    tile[s_ ^ 1u] = (X).b;                            \
+  }
+        QCSIM_QFT_PUT(0, x0) QCSIM_QFT_PUT(1, x1) QCSIM_QFT_PUT(2, x2) QCSIM_QFT_PUT(3, x3)
+        QCSIM_QFT_PUT(4, x4) QCSIM_QFT_PUT(5, x5) QCSIM_QFT_PUT(6, x6) QCSIM_QFT_PUT(7, x7)
+#undef QCSIM_QFT_PUT
+      } else {
 #pragma unroll 1
-      for (uint32_t it0 = 0; it0 < n_it; it0 += 4) {  // 4 loads in flight per thread (x 3 CTAs per SM)
-        amp2 x[4];
-#pragma unroll
-        for (uint32_t u = 0; u < 4; ++u) {
-          const uint32_t lv = (it0 + u) << 9;
+        for (uint32_t it = 0; it < n_it; ++it) {
+          const uint32_t lv = it << 9;
           uint64_t gv = 0;
 #pragma unroll 1
           for (int j = 9; j < k; ++j) gv |= (uint64_t)((lv >> j) & 1u) << A.tpos[j];
-          if (it0 + u < n_it) x[u] = ld_amp2(psi + (gbase | g_fixed | gv));
-        }
-#pragma unroll
-        for (uint32_t u = 0; u < 4; ++u) {
-          if (it0 + u >= n_it) continue;
-          const uint32_t s = s_fixed ^ swz((it0 + u) << 9);
-          tile[s] = x[u].a;
-          tile[s ^ 1u] = x[u].b;
+          const amp2 x = ld_amp2(psi + (gbase | g_fixed | gv));
+          const uint32_t s = s_fixed ^ swz(lv);
+          tile[s] = x.a;
+          tile[s ^ 1u] = x.b;
         }
       }
     }
@@ -228,14 +244,16 @@ static __global__ void __launch_bounds__(kTileThreads, 3) k_qft_pass(amp* __rest
       const amp p_cta = tw_cta[gi];
 #pragma unroll 1
       for (uint32_t item = tid; item < items; item += kTileThreads) {
-        const uint32_t lbase = qft_lbase(grp, item);
         amp P;
+        uint32_t sl;
         if (tabled) {
           P = cmul(p_cta, __ldg(tw_item + gi * kQftItemsMax + item));
+          sl = __ldg(slot_item + gi * kQftItemsMax + item);
         } else {
+          const uint32_t lbase = qft_lbase(grp, item);
           P = qft_base(A, grp, qft_logical(A, gbase | A.rank_bits | qft_phys_of_local(A, lbase)), inverse);
+          sl = swz(lbase);
         }
-        const uint32_t sl = swz(lbase);
         amp v[8];
         if (G == 3) {
 #pragma unroll
@@ -261,17 +279,30 @@ static __global__ void __launch_bounds__(kTileThreads, 3) k_qft_pass(amp* __rest
     }
 
     if (mover) {
+      if (n_it == 8) {
+        const uint64_t g9 = 1ULL << A.tpos[9], g10 = 1ULL << A.tpos[10], g11 = 1ULL << A.tpos[11];
+        amp* dst = psi + (gbase | g_fixed);
+#pragma unroll
+        for (uint32_t it = 0; it < 8; ++it) {
+          const uint32_t s = s_fixed ^ swz(it << 9);
+          amp2 x;
+          x.a = tile[s];
+          x.b = tile[s ^ 1u];
+          st_amp2(dst + (((it & 1u) ? g9 : 0ULL) | ((it & 2u) ? g10 : 0ULL) | ((it & 4u) ? g11 : 0ULL)), x);
+        }
+      } else {
 #pragma unroll 1
-      for (uint32_t it = 0; it < n_it; ++it) {
-        const uint32_t lv = it << 9;
-        uint64_t gv = 0;
+        for (uint32_t it = 0; it < n_it; ++it) {
+          const uint32_t lv = it << 9;
+          uint64_t gv = 0;
 #pragma unroll 1
-        for (int j = 9; j < k; ++j) gv |= (uint64_t)((lv >> j) & 1u) << A.tpos[j];
-        const uint32_t s = s_fixed ^ swz(lv);
-        amp2 x;
-        x.a = tile[s];
-        x.b = tile[s ^ 1u];
-        st_amp2(psi + (gbase | g_fixed | gv), x);
+          for (int j = 9; j < k; ++j) gv |= (uint64_t)((lv >> j) & 1u) << A.tpos[j];
+          const uint32_t s = s_fixed ^ swz(lv);
+          amp2 x;
+          x.a = tile[s];
+          x.b = tile[s ^ 1u];
+          st_amp2(psi + (gbase | g_fixed | gv), x);
+        }
       }
     }
     __syncthreads();

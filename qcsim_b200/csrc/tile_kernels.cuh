@@ -79,7 +79,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // with cp.async while the rounds of the current one run -- measured slightly slower on B200 in
 // round 1 (39.5 vs 36.8 ms per 30-qubit layer: 8 warps per SM do not cover the LDS latency of the
 // matrix loads), kept for the next round's tuning.
-__global__ void __launch_bounds__(kTileThreads, 2) k_tile_pass(amp* __restrict__ psi, const __grid_constant__ TilePassArgs A) {
+static __global__ void __launch_bounds__(kTileThreads, 2) k_tile_pass(amp* __restrict__ psi, const __grid_constant__ TilePassArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   amp* tile = reinterpret_cast<amp*>(smem_raw);
   const int k = A.k;

@@ -49,11 +49,10 @@ constexpr int kPipeThreads = kPipeConsumers + 32;        // + producer warp
 constexpr int kPipeLookahead = 4;                        // tiles requested ahead of the one being drained
 constexpr uint32_t kPipeTileBytes = (uint32_t)sizeof(amp) << kPipeTileBits;
 
-struct PipePassArgs {
+// what the producer warp needs: the tensor map and how tile numbers / TMA ops turn into coordinates
+struct PipeGeom {
   CUtensorMap tmap;              // rank 5: dim 0 = qubits 0..2 (16 doubles), dims 1..4 = tile-qubit groups
   uint64_t n_tiles;
-  int n_rounds;
-  int n_mats;
   int n_enum;                    // tile qubits not covered by the TMA box: 2^n_enum ops per tile
   int box_bytes;                 // bytes one TMA op moves
   int dim_lo[5];                 // lowest index bit of tensor dimension i
@@ -61,6 +60,13 @@ struct PipePassArgs {
   int enum_pos[9];               // index bit of enumerated tile qubit j
   int sorted_pos[kPipeTileBits]; // tile qubits ascending (to scatter the tile number around them)
   int slot_pos[kPipeTileBits];   // index bit held by shared-memory slot bit j
+  int pad;
+};
+
+struct PipePassArgs {
+  PipeGeom geom;
+  int n_rounds;
+  int n_mats;
   TileRoundDesc rounds[kMaxTileRounds];
   double2 mats[kMaxTileMats * kRoundMatAmps];
 };
@@ -129,93 +135,121 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
 }
 }  // namespace pipe
 
+namespace pipe {
+
+// scatter the tile number into the non-tile index bits
+__device__ __forceinline__ uint64_t gbase_of(const PipeGeom& G, uint64_t t) {
+  uint64_t g = t;
+#pragma unroll
+  for (int j = 0; j < kPipeTileBits; ++j) g = insert_zero(g, G.sorted_pos[j]);
+  return g;
+}
+
+// carve the dynamic shared memory: 6 tile buffers (1024 B aligned: the 128 B swizzle pattern is a function of the
+// shared-memory ADDRESS) | 28 KiB of per-pass tables (round matrices / twiddle tables) | mbarriers
+struct Smem {
+  amp* tiles;
+  amp* tables;
+  uint64_t* full;  // [stage]: the tile has landed (TMA transaction bytes)
+  uint64_t* done;  // [stage]: the consumers have finished the rounds
+};
+__device__ __forceinline__ Smem carve(unsigned char* raw) {
+  Smem m;
+  unsigned char* const al = raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u);
+  m.tiles = reinterpret_cast<amp*>(al);
+  m.tables = m.tiles + (size_t)kPipeStages * (1u << kPipeTileBits);
+  m.full = reinterpret_cast<uint64_t*>(m.tables + (size_t)kMaxTileMats * kRoundMatAmps);
+  m.done = m.full + kPipeStages;
+  return m;
+}
+__device__ __forceinline__ void init_barriers(const Smem& m) {
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kPipeStages; ++s) {
+      mbar_init(&m.full[s], 1);
+      mbar_init(&m.done[s], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+}
+
+// the producer warp: all tile movement of the CTA
+__device__ __forceinline__ void producer(const PipeGeom& G, const Smem& m) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t n_ops = 1u << G.n_enum;
+  const uint32_t box_amps = (uint32_t)G.box_bytes / (uint32_t)sizeof(amp);
+  auto coords_of = [&](uint64_t gbase, uint32_t e, int* c) {
+    uint64_t idx = gbase;
+#pragma unroll 1
+    for (int j = 0; j < G.n_enum; ++j) idx |= (uint64_t)((e >> j) & 1u) << G.enum_pos[j];
+    c[0] = 0;
+#pragma unroll
+    for (int d = 1; d < 5; ++d) c[d] = (int)((idx >> G.dim_lo[d]) & ((1ULL << G.dim_mask_bits[d]) - 1ULL));
+  };
+  auto issue_load = [&](uint64_t t, int s) {
+    if (lane == 0) mbar_arrive_expect_tx(&m.full[s], kPipeTileBytes);
+    __syncwarp();
+    const uint64_t gbase = gbase_of(G, t);
+    amp* dst = m.tiles + (size_t)s * (1u << kPipeTileBits);
+    for (uint32_t e = lane; e < n_ops; e += 32) {
+      int c[5];
+      coords_of(gbase, e, c);
+      tma_load_5d(dst + (size_t)e * box_amps, &G.tmap, &m.full[s], c[0], c[1], c[2], c[3], c[4]);
+    }
+  };
+  auto issue_store = [&](uint64_t t, int s) {
+    const uint64_t gbase = gbase_of(G, t);
+    const amp* src = m.tiles + (size_t)s * (1u << kPipeTileBits);
+    for (uint32_t e = lane; e < n_ops; e += 32) {
+      int c[5];
+      coords_of(gbase, e, c);
+      tma_store_5d(src + (size_t)e * box_amps, &G.tmap, c[0], c[1], c[2], c[3], c[4]);
+    }
+    bulk_commit();  // every lane closes its own (possibly empty) group: group counts stay aligned across lanes
+  };
+  const uint64_t step = gridDim.x;
+  // prologue: kPipeLookahead tiles in flight before the consumers start
+#pragma unroll 1
+  for (int j = 0; j < kPipeLookahead; ++j)
+    if (blockIdx.x + j * step < G.n_tiles) issue_load(blockIdx.x + j * step, j);
+  uint32_t i = 0;
+  for (uint64_t t = blockIdx.x; t < G.n_tiles; t += step, ++i) {
+    const int s = (int)(i % kPipeStages);
+    mbar_wait(&m.done[s], (i / kPipeStages) & 1u);  // rounds of tile i finished, fenced for the async proxy
+    issue_store(t, s);
+    const uint64_t t2 = t + kPipeLookahead * step;
+    if (t2 < G.n_tiles) {
+      // the buffer of tile i + lookahead is the one tile i + lookahead - stages drained from: wait until that
+      // drain has been read out of shared memory (all but the most recent stages - lookahead groups)
+      bulk_wait_read<kPipeStages - kPipeLookahead>();
+      __syncwarp();
+      issue_load(t2, (int)((i + kPipeLookahead) % kPipeStages));
+    }
+  }
+  bulk_wait<0>();  // all stores complete before the CTA exits
+}
+
+}  // namespace pipe
+
 // Dynamic shared memory (1024 B aligned): 6 tile buffers | round matrices | mbarriers.
 static __global__ void __launch_bounds__(kPipeThreads, 1) k_tile_pipe(const __grid_constant__ PipePassArgs A) {
   using namespace pipe;
   extern __shared__ __align__(16) unsigned char pipe_smem[];
-  // the 128 B swizzle pattern is a function of the shared-memory ADDRESS: tile buffers start on a 1024 B boundary
-  unsigned char* const smem_al = pipe_smem + ((1024u - (smem_u32(pipe_smem) & 1023u)) & 1023u);
-  amp* const tiles = reinterpret_cast<amp*>(smem_al);
-  amp* const smats = tiles + (size_t)kPipeStages * (1u << kPipeTileBits);
-  uint64_t* const bars = reinterpret_cast<uint64_t*>(smats + (size_t)kMaxTileMats * kRoundMatAmps);
-  uint64_t* const full = bars;                 // [stage]: the tile has landed (TMA transaction bytes)
-  uint64_t* const done = bars + kPipeStages;   // [stage]: the consumers have finished the rounds
+  const Smem sm = carve(pipe_smem);
+  amp* const tiles = sm.tiles;
+  amp* const smats = sm.tables;
+  uint64_t* const full = sm.full;
+  uint64_t* const done = sm.done;
   const uint32_t tid = threadIdx.x;
   const uint32_t warp = tid >> 5, lane = tid & 31u;
-
-  if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < kPipeStages; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&done[s], 1);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
+  init_barriers(sm);
   // round matrices: parameter block -> shared memory once per CTA (a lane reads two entries per round; per-lane
   // addresses would serialise in the constant cache)
   for (uint32_t i = tid; i < (uint32_t)A.n_mats * kRoundMatAmps; i += kPipeThreads) smats[i] = A.mats[i];
   __syncthreads();
 
-  auto gbase_of = [&](uint64_t t) {  // scatter the tile number into the non-tile index bits
-    uint64_t g = t;
-#pragma unroll
-    for (int j = 0; j < kPipeTileBits; ++j) g = insert_zero(g, A.sorted_pos[j]);
-    return g;
-  };
-
   if (warp == kPipeConsumerWarps) {
-    // ------------------------------- producer warp: all tile movement -------------------------------
-    const uint32_t n_ops = 1u << A.n_enum;
-    const uint32_t box_amps = (uint32_t)A.box_bytes / (uint32_t)sizeof(amp);
-    auto coords_of = [&](uint64_t gbase, uint32_t e, int* c) {
-      uint64_t idx = gbase;
-#pragma unroll 1
-      for (int j = 0; j < A.n_enum; ++j) idx |= (uint64_t)((e >> j) & 1u) << A.enum_pos[j];
-      c[0] = 0;
-#pragma unroll
-      for (int d = 1; d < 5; ++d) c[d] = (int)((idx >> A.dim_lo[d]) & ((1ULL << A.dim_mask_bits[d]) - 1ULL));
-    };
-    auto issue_load = [&](uint64_t t, int s) {
-      if (lane == 0) mbar_arrive_expect_tx(&full[s], kPipeTileBytes);
-      __syncwarp();
-      const uint64_t gbase = gbase_of(t);
-      amp* dst = tiles + (size_t)s * (1u << kPipeTileBits);
-      for (uint32_t e = lane; e < n_ops; e += 32) {
-        int c[5];
-        coords_of(gbase, e, c);
-        tma_load_5d(dst + (size_t)e * box_amps, &A.tmap, &full[s], c[0], c[1], c[2], c[3], c[4]);
-      }
-    };
-    auto issue_store = [&](uint64_t t, int s) {
-      const uint64_t gbase = gbase_of(t);
-      const amp* src = tiles + (size_t)s * (1u << kPipeTileBits);
-      for (uint32_t e = lane; e < n_ops; e += 32) {
-        int c[5];
-        coords_of(gbase, e, c);
-        tma_store_5d(src + (size_t)e * box_amps, &A.tmap, c[0], c[1], c[2], c[3], c[4]);
-      }
-      bulk_commit();  // every lane closes its own (possibly empty) group: group counts stay aligned across lanes
-    };
-    const uint64_t step = gridDim.x;
-    // prologue: kPipeLookahead tiles in flight before the consumers start
-#pragma unroll 1
-    for (int j = 0; j < kPipeLookahead; ++j)
-      if (blockIdx.x + j * step < A.n_tiles) issue_load(blockIdx.x + j * step, j);
-    uint32_t i = 0;
-    for (uint64_t t = blockIdx.x; t < A.n_tiles; t += step, ++i) {
-      const int s = (int)(i % kPipeStages);
-      mbar_wait(&done[s], (i / kPipeStages) & 1u);  // rounds of tile i finished, fenced for the async proxy
-      issue_store(t, s);
-      const uint64_t t2 = t + kPipeLookahead * step;
-      if (t2 < A.n_tiles) {
-        // the buffer of tile i + lookahead is the one tile i + lookahead - stages drained from: wait until that
-        // drain has been read out of shared memory (all but the most recent stages - lookahead groups)
-        bulk_wait_read<kPipeStages - kPipeLookahead>();
-        __syncwarp();
-        issue_load(t2, (int)((i + kPipeLookahead) % kPipeStages));
-      }
-    }
-    bulk_wait<0>();  // all stores complete before the CTA exits
+    producer(A.geom, sm);
     return;
   }
 
@@ -276,10 +310,10 @@ static __global__ void __launch_bounds__(kPipeThreads, 1) k_tile_pipe(const __gr
     }
   }
 
-  for (uint64_t t = blockIdx.x + (uint64_t)group * gridDim.x, i = group; t < A.n_tiles; t += (uint64_t)kPipeGroups * gridDim.x, i += kPipeGroups) {
+  for (uint64_t t = blockIdx.x + (uint64_t)group * gridDim.x, i = group; t < A.geom.n_tiles; t += (uint64_t)kPipeGroups * gridDim.x, i += kPipeGroups) {
     const int s = (int)(i % kPipeStages);
     amp* const tile = tiles + (size_t)s * (1u << kPipeTileBits);
-    const uint64_t gbase = gbase_of(t);
+    const uint64_t gbase = gbase_of(A.geom, t);
     mbar_wait(&full[s], (uint32_t)(i / kPipeStages) & 1u);
 
 #pragma unroll 1
