@@ -34,7 +34,7 @@ int env_int(const char* name, int dflt) {
 
 constexpr size_t kPipeSmemBytes =
     1024 /* alignment slack */ + (size_t)kPipeStages * kPipeTileBytes + (size_t)kMaxTileMats * kRoundMatAmps * sizeof(amp) +
-    2 * kPipeStages * sizeof(uint64_t);
+    2 * kPipeStages * sizeof(uint64_t) + kMaxTileRounds * sizeof(RoundTable);
 static_assert(kPipeSmemBytes <= 227 * 1024, "shared memory per CTA");
 
 int fusion_init_device_kernels() {  // per device, from engine_create

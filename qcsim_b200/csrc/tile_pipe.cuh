@@ -231,7 +231,13 @@ __device__ __forceinline__ void producer(const PipeGeom& G, const Smem& m) {
 
 }  // namespace pipe
 
-// Dynamic shared memory (1024 B aligned): 6 tile buffers | round matrices | mbarriers.
+// per-round lookup tables of k_tile_pipe (shared memory, filled once per CTA)
+struct RoundTable {
+  uint32_t load_g[8], store_g[8], load_t[4], store_t[4], warp_hi[8], warp_ms[8];
+  uint32_t x_hi, x_i0, x_p0, x_p1;
+};
+
+// Dynamic shared memory (1024 B aligned): 6 tile buffers | round matrices | mbarriers | round tables.
 static __global__ void __launch_bounds__(kPipeThreads, 1) k_tile_pipe(const __grid_constant__ PipePassArgs A) {
   using namespace pipe;
   extern __shared__ __align__(16) unsigned char pipe_smem[];
@@ -271,44 +277,52 @@ static __global__ void __launch_bounds__(kPipeThreads, 1) k_tile_pipe(const __gr
   const uint32_t g = lane >> 2, tq = lane & 3u;
   const uint32_t group = warp / kPipeGroupWarps, gwarp = warp % kPipeGroupWarps;
 
-  // Everything about a round that does not depend on the tile is computed ONCE per thread: the swizzled slots of
-  // its fragment loads / result stores, the slot strides of the panel / register / column bits, and the part of
-  // the variant index that comes from tile bits (warp-index bits).  The per-tile round body is then loads, 32
-  // DMMA, stores, barrier -- no dependent integer chain in front of the loads.
-  // (packed: slots are 11-bit numbers)  ls = load slot | store slot << 16, xa = x_hi | x_i0 << 16, xb = x_p0 | x_p1 << 16,
-  // ms = outside-tile variant selectors (3 bytes) | matrix base << 24
-  uint32_t ls[kMaxTileRounds], xa[kMaxTileRounds], xb[kMaxTileRounds], ms[kMaxTileRounds];
-#pragma unroll 1
-  for (int r = 0; r < kMaxTileRounds; ++r) {
-    ls[r] = xa[r] = xb[r] = ms[r] = 0;
-    if (r < A.n_rounds) {
-      const TileRoundDesc rd = A.rounds[r];
-      const uint32_t rb0 = 1u << (rd.rb & 31u), rb1 = 1u << ((rd.rb >> 8) & 31u), rb2 = 1u << ((rd.rb >> 16) & 31u);
-      auto ib = [&](int j) { return 1u << ((rd.tb[j >> 2] >> (8 * (j & 3))) & 31u); };  // slot bit walked by item bit j
-      uint32_t hi = 0;  // warp part of the item index (plain slot bits)
-#pragma unroll
-      for (int j = 0; j < 3; ++j) hi |= ((gwarp >> j) & 1u) ? ib(5 + j) : 0u;
+  // Everything about a round that does not depend on the tile is tabulated ONCE per CTA in shared memory: the
+  // swizzled slot of a lane's fragment loads / result stores is the XOR of a part chosen by its column / row index g,
+  // a part chosen by its k-lane tq and a part chosen by its warp (the swizzle is linear over XOR); plus the slot strides
+  // of the panel / register / column bits and, per warp, the matrix it uses.  (Per-thread arrays indexed by the round
+  // went to local memory, and with all of L1 carved out as shared memory every such load was an L2 round trip at the
+  // head of every round.)
+  RoundTable* const rt = reinterpret_cast<RoundTable*>(sm.done + kPipeStages);
+  for (uint32_t e = tid; e < (uint32_t)A.n_rounds * 48u; e += kPipeThreads) {
+    const uint32_t r = e / 48u, j = e % 48u;
+    const TileRoundDesc rd = A.rounds[r];
+    const uint32_t rb0 = 1u << (rd.rb & 31u), rb1 = 1u << ((rd.rb >> 8) & 31u), rb2 = 1u << ((rd.rb >> 16) & 31u);
+    auto ib = [&](int q) { return 1u << ((rd.tb[q >> 2] >> (8 * (q & 3))) & 31u); };  // slot bit walked by item bit q
+    if (j < 8) {  // loads: item g of the panel
+      rt[r].load_g[j] = tswz(((j & 1u) ? ib(0) : 0u) | ((j & 2u) ? ib(1) : 0u) | ((j & 4u) ? ib(2) : 0u));
+    } else if (j < 16) {  // stores: amplitude g
+      const uint32_t x = j - 8;
+      rt[r].store_g[x] = tswz(((x & 1u) ? rb0 : 0u) | ((x & 2u) ? rb1 : 0u) | ((x & 4u) ? rb2 : 0u));
+    } else if (j < 20) {  // loads: amplitudes tq (+4)
+      const uint32_t x = j - 16;
+      rt[r].load_t[x] = tswz(((x & 1u) ? rb0 : 0u) | ((x & 2u) ? rb1 : 0u));
+    } else if (j < 24) {  // stores: items 2 tq (+1)
+      const uint32_t x = j - 20;
+      rt[r].store_t[x] = tswz(((x & 1u) ? ib(1) : 0u) | ((x & 2u) ? ib(2) : 0u));
+    } else if (j < 32) {  // warp part of the item index, and the matrix the warp uses
+      const uint32_t w = j - 24;
+      uint32_t hi = 0;
+      for (int q = 0; q < 3; ++q) hi |= ((w >> q) & 1u) ? ib(5 + q) : 0u;
       const int nvar = rd.var & 0xff;
       uint32_t vidx = 0, gs = 0;
-#pragma unroll
-      for (int j = 0; j < kMaxVariantBits; ++j) {
-        const uint32_t e = (rd.var >> (8 + 8 * j)) & 0xffu;
-        if (j < nvar) {
-          if (e & 1u) gs |= (0x80u | (e >> 1)) << (8 * j);  // index bit outside the tile: resolved per tile
-          else vidx |= ((hi >> (e >> 1)) & 1u) << j;
+      for (int q = 0; q < kMaxVariantBits; ++q) {
+        const uint32_t en = (rd.var >> (8 + 8 * q)) & 0xffu;
+        if (q < nvar) {
+          if (en & 1u) gs |= (0x80u | (en >> 1)) << (8 * q);  // index bit outside the tile: resolved per tile
+          else vidx |= ((hi >> (en >> 1)) & 1u) << q;
         }
       }
-      ms[r] = gs | ((rd.mat_off + vidx) << 24);
-      // slots: loads -- item g of the panel, amplitudes tq (+4); stores -- items 2 tq (+1), amplitude g
-      const uint32_t l0 = tswz(hi | ((g & 1u) ? ib(0) : 0u) | ((g & 2u) ? ib(1) : 0u) | ((g & 4u) ? ib(2) : 0u) | ((tq & 1u) ? rb0 : 0u) |
-                               ((tq & 2u) ? rb1 : 0u));
-      const uint32_t s0 = tswz(hi | ((tq & 1u) ? ib(1) : 0u) | ((tq & 2u) ? ib(2) : 0u) | ((g & 1u) ? rb0 : 0u) | ((g & 2u) ? rb1 : 0u) |
-                               ((g & 4u) ? rb2 : 0u));
-      ls[r] = l0 | (s0 << 16);
-      xa[r] = tswz(rb2) | (tswz(ib(0)) << 16);
-      xb[r] = tswz(ib(3)) | (tswz(ib(4)) << 16);
+      rt[r].warp_hi[w] = tswz(hi);
+      rt[r].warp_ms[w] = gs | ((rd.mat_off + vidx) << 24);
+    } else if (j == 32) {
+      rt[r].x_hi = tswz(rb2);
+      rt[r].x_i0 = tswz(ib(0));
+      rt[r].x_p0 = tswz(ib(3));
+      rt[r].x_p1 = tswz(ib(4));
     }
   }
+  asm volatile("bar.sync 3, %0;" ::"n"(kPipeConsumers) : "memory");  // all consumers (the producer is already moving tiles)
 
   for (uint64_t t = blockIdx.x + (uint64_t)group * gridDim.x, i = group; t < A.geom.n_tiles; t += (uint64_t)kPipeGroups * gridDim.x, i += kPipeGroups) {
     const int s = (int)(i % kPipeStages);
@@ -319,17 +333,19 @@ static __global__ void __launch_bounds__(kPipeThreads, 1) k_tile_pipe(const __gr
 #pragma unroll 1
     for (int r = 0; r < A.n_rounds; ++r) {
       {
-        uint32_t midx = ms[r] >> 24;
-        const uint32_t ld0 = ls[r] & 0xffffu, st0 = ls[r] >> 16;
+        const RoundTable& T = rt[r];
+        const uint32_t wh = T.warp_hi[gwarp], wm = T.warp_ms[gwarp];
+        const uint32_t ld0 = wh ^ T.load_g[g] ^ T.load_t[tq], st0 = wh ^ T.store_g[g] ^ T.store_t[tq];
+        uint32_t midx = wm >> 24;
 #pragma unroll
         for (int j = 0; j < kMaxVariantBits; ++j) {
-          const uint32_t e = (ms[r] >> (8 * j)) & 0xffu;
+          const uint32_t e = (wm >> (8 * j)) & 0xffu;
           if (e & 0x80u) midx += (uint32_t)((gbase >> (e & 0x7fu)) & 1ULL) << j;
         }
         // A fragments of this warp's matrix
         const amp* __restrict__ M = smats + (size_t)midx * kRoundMatAmps;
         const double2 m_lo = M[g * 8 + tq], m_hi = M[g * 8 + 4 + tq];
-        const uint32_t x_hi = xa[r] & 0xffffu, x_i0 = xa[r] >> 16, x_p0 = xb[r] & 0xffffu, x_p1 = xb[r] >> 16;
+        const uint32_t x_hi = T.x_hi, x_i0 = T.x_i0, x_p0 = T.x_p0, x_p1 = T.x_p1;
         const double* const td = reinterpret_cast<const double*>(tile);
         double* const tdw = reinterpret_cast<double*>(tile);
         const uint32_t lq = tq & 1u, sq = g & 1u;  // half taken first by this lane's loads / stores (0 = real)
