@@ -246,9 +246,9 @@ def run_ours(args):
     passes = max(int(st["state_passes"]), 1)
     avg_launch_ms = ms / passes  # the timed region is back-to-back state passes on one stream
     if args.workload == "qft":
-        dominant = "k_qft_pass (radix-8 FFT pass) + k_tile_permute (qubit reversal)"
+        dominant = "k_qft_pipe (TMA-staged radix-8/4/2 QFT pass) + k_bit_reverse (qubit reversal)"
     elif args.fusion:
-        dominant = "k_tile_pass (fused gate block: dense 8x8 rounds on a shared-memory tile)"
+        dominant = "k_tile_pipe (fused gate block: TMA-staged tiles, DMMA 16x16 real rounds, mbarrier ring)"
     else:
         dominant = "single-gate passes (k_pair_v2 dominant)"
     traffic = None
@@ -266,8 +266,12 @@ def run_ours(args):
         "bytes_per_step": algo_bytes // max(K, 1), "passes_per_step": st["state_passes"] / max(K, 1),
         "rounds_per_step": st.get("fused_rounds", 0) / max(K, 1),
         "nominal_peak_frac": round(achieved / 8000.0, 4),
-        "note": ("fused passes trade HBM passes for fp64 work: each round is 32 DFMA per amplitude, so a pass of r rounds "
-                 "is fp64-pipe bound beyond ~3 rounds; the unfused single-gate kernels in `kernels` are the HBM-bound ones"),
+        "note": ("fused passes trade HBM passes for fp64 work: a round is a 16x16 real matrix product per 8 amplitudes (32 FMA per "
+                 "amplitude) on the FP64 tensor path (DMMA, 64 FMA/clk/SM); a pass of r rounds is fp64-bound beyond ~3 rounds, so "
+                 "frac < 1 here is fp64 time, not wasted HBM traffic; the unfused single-gate kernels in `kernels` are the HBM-bound ones"),
+        "fp64": {"fma_per_amp_per_round": 32, "fma_per_step": int(32 * st.get("fused_rounds", 0) / max(K, 1) * (1 << (n - log2w))),
+                 "achieved_tflops": round(2 * 32 * st.get("fused_rounds", 0) * (1 << (n - log2w)) / (ms * 1e-3) / 1e12, 2) if args.workload == "random" else None,
+                 "peak_tflops_fp64": 37.2},
     }
 
     result = {
@@ -287,7 +291,10 @@ def run_ours(args):
         "roofline": roofline,
         "kernels": kernels,
         "check": {"norm2": norm2},
-        "exchange": {"calls": st["exchange_calls"], "bytes": st["exchange_bytes"], "ms": st["exchange_ms"]},
+        "exchange": {"calls": st["exchange_calls"], "bytes": st["exchange_bytes"], "ms": st["exchange_ms"],
+                     "GBps_per_direction": round(st["exchange_bytes"] / (st["exchange_ms"] * 1e-3) / 1e9, 1) if st["exchange_ms"] else None,
+                     "frac_of_nvlink_900": round(st["exchange_bytes"] / (st["exchange_ms"] * 1e-3) / 1e9 / 900.0, 3) if st["exchange_ms"] else None,
+                     "note": "bytes this rank sent over NVLink by the in-place exchange kernel (global<->local qubit swaps), CUDA-event time"},
     }
     reg.close()
     if world == 1 and not args.no_kernel_sweep and args.sweep_big_qubits > n:
