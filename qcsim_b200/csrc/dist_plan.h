@@ -160,21 +160,16 @@ inline std::vector<DistStep> dist_plan(DistLayout& L, const std::vector<Op>& ops
   }
   const int N = (int)ops.size();
 
-  // 2. next non-diagonal use of every logical qubit
-  std::vector<std::vector<int>> uses(n);
-  std::vector<uint64_t> nd(N);
-  for (int i = 0; i < N; ++i) {
-    nd[i] = masks_of(ops[i]).nd;
-    for (int q = 0; q < n; ++q)
-      if ((nd[i] >> q) & 1ULL) uses[q].push_back(i);
-  }
-  std::vector<size_t> cursor(n, 0);
+  // 2. Rounds of "everything that can run locally, then one exchange".  Walking the pending ops in program order, an
+  //    op runs now when every qubit it acts on non-diagonally is local AND it commutes with every op deferred before
+  //    it (same rule as plan_passes: two ops commute when on every shared qubit both act diagonally); otherwise it is
+  //    deferred.  So an exchange is not a barrier for unrelated gates: later gates on other qubits are pulled in front
+  //    of it, which keeps the fused passes full and lets one exchange serve every global qubit the deferred ops need.
+  std::vector<OpMasks> mk(N);
+  for (int i = 0; i < N; ++i) mk[i] = masks_of(ops[i]);
+  std::vector<int> pending(N);
+  for (int i = 0; i < N; ++i) pending[i] = i;
   const int kNever = 1 << 30;
-  auto next_use = [&](int q, int i) {
-    size_t& c = cursor[q];
-    while (c < uses[q].size() && uses[q][c] < i) ++c;
-    return c < uses[q].size() ? uses[q][c] : kNever;
-  };
 
   DistStep cur;
   auto flush_local = [&]() {
@@ -182,53 +177,68 @@ inline std::vector<DistStep> dist_plan(DistLayout& L, const std::vector<Op>& ops
     cur = DistStep();
   };
 
-  for (int i = 0; i < N; ++i) {
-    const Op& op = ops[i];
-    bool needs_global = false;
+  while (!pending.empty()) {
+    uint64_t global_mask = 0;
     for (int q = 0; q < n; ++q)
-      if (((nd[i] >> q) & 1ULL) && L.is_global(q)) needs_global = true;
-    if (needs_global) {
-      // incoming: global-resident logical qubits by next use; outgoing: local ones, farthest first
-      std::vector<std::pair<int, int>> incoming, outgoing;  // (next use, logical)
-      for (int q = 0; q < n; ++q) {
-        const int nu = next_use(q, i);
-        if (L.is_global(q)) incoming.push_back({nu, q});
-        else if (!((nd[i] >> q) & 1ULL)) outgoing.push_back({nu, q});
+      if (L.is_global(q)) global_mask |= 1ULL << q;
+    uint64_t blocked_nd = 0, blocked_dg = 0;
+    std::vector<int> deferred;
+    for (int i : pending) {
+      const OpMasks& m = mk[i];
+      const bool needs_global = (m.nd & global_mask) != 0;
+      const bool conflict = ((m.nd | m.dg) & blocked_nd) != 0 || (m.nd & blocked_dg) != 0;
+      if (!needs_global && !conflict) {
+        Op phys;
+        if (fold_to_physical(ops[i], L, rank, &phys)) cur.ops.push_back(phys);
+      } else {
+        deferred.push_back(i);
+        blocked_nd |= m.nd;
+        blocked_dg |= m.dg;
       }
-      std::sort(incoming.begin(), incoming.end());
-      // farthest next use first; positions below kMinExchangePos only when nothing else is left (short
-      // runs over NVLink); ties: the qubit highest up (longest contiguous runs)
-      const int min_pos = std::min(kMinExchangePos, std::max(0, nl - g - 1));
-      std::sort(outgoing.begin(), outgoing.end(), [&](const std::pair<int, int>& a, const std::pair<int, int>& b) {
-        const bool la = L.phys_of[a.second] < min_pos, lb = L.phys_of[b.second] < min_pos;
-        if (la != lb) return lb;
-        if (a.first != b.first) return a.first > b.first;
-        return L.phys_of[a.second] > L.phys_of[b.second];
-      });
-      int k = 0;
-      std::vector<int> in_q, out_q;
-      for (size_t j = 0; j < incoming.size() && j < outgoing.size() && (int)j < g && (int)j < kMaxExchange; ++j) {
-        const bool mandatory = incoming[j].first == i;
-        if (!mandatory && !(incoming[j].first < outgoing[j].first)) break;
-        in_q.push_back(incoming[j].second);
-        out_q.push_back(outgoing[j].second);
-        ++k;
-      }
-      flush_local();
-      DistStep ex;
-      ex.exchange = true;
-      ex.k = k;
-      for (int j = 0; j < k; ++j) {
-        ex.gpos[j] = L.phys_of[in_q[j]];
-        ex.lpos[j] = L.phys_of[out_q[j]];
-      }
-      steps.push_back(ex);
-      for (int j = 0; j < k; ++j) L.swap_physical(ex.gpos[j], ex.lpos[j]);
     }
-    Op phys;
-    if (fold_to_physical(op, L, rank, &phys)) cur.ops.push_back(phys);
+    flush_local();
+    if (deferred.empty()) break;
+    // first non-diagonal use of every logical qubit among the deferred ops
+    std::vector<int> first_use(n, kNever);
+    for (size_t d = 0; d < deferred.size(); ++d)
+      for (int q = 0; q < n; ++q)
+        if (((mk[deferred[d]].nd >> q) & 1ULL) && first_use[q] == kNever) first_use[q] = (int)d;
+    const uint64_t mandatory = mk[deferred[0]].nd & global_mask;  // the first deferred op is one that needs a global qubit
+    // incoming: global-resident qubits by first use; outgoing: local ones, farthest first use first; positions below
+    // kMinExchangePos only when nothing else is left (short runs over NVLink); ties: the qubit highest up
+    std::vector<std::pair<int, int>> incoming, outgoing;  // (first use, logical)
+    for (int q = 0; q < n; ++q) {
+      if (L.is_global(q)) incoming.push_back({((mandatory >> q) & 1ULL) ? -1 : first_use[q], q});
+      else outgoing.push_back({first_use[q], q});
+    }
+    std::sort(incoming.begin(), incoming.end());
+    const int min_pos = std::min(kMinExchangePos, std::max(0, nl - g - 1));
+    std::sort(outgoing.begin(), outgoing.end(), [&](const std::pair<int, int>& a, const std::pair<int, int>& b) {
+      const bool la = L.phys_of[a.second] < min_pos, lb = L.phys_of[b.second] < min_pos;
+      if (la != lb) return lb;
+      if (a.first != b.first) return a.first > b.first;
+      return L.phys_of[a.second] > L.phys_of[b.second];
+    });
+    int k = 0;
+    std::vector<int> in_q, out_q;
+    for (size_t j = 0; j < incoming.size() && j < outgoing.size() && (int)j < g && (int)j < kMaxExchange; ++j) {
+      const bool must = incoming[j].first < 0;
+      if (!must && !(incoming[j].first < outgoing[j].first)) break;
+      in_q.push_back(incoming[j].second);
+      out_q.push_back(outgoing[j].second);
+      ++k;
+    }
+    DistStep ex;
+    ex.exchange = true;
+    ex.k = k;
+    for (int j = 0; j < k; ++j) {
+      ex.gpos[j] = L.phys_of[in_q[j]];
+      ex.lpos[j] = L.phys_of[out_q[j]];
+    }
+    steps.push_back(ex);
+    for (int j = 0; j < k; ++j) L.swap_physical(ex.gpos[j], ex.lpos[j]);
+    pending.swap(deferred);
   }
-  flush_local();
 
   // 3. account for the relabellings: logical q now names the data that was called sigma[q]
   int new_phys[64];

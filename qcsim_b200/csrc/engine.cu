@@ -228,14 +228,26 @@ int engine_masked_norm2(qcsim_sv* h, uint64_t mask, uint64_t want, double* out) 
   // logical (mask, want) -> physical bit positions of the current layout
   uint64_t pmask = mask, pwant = want;
   if (h->world > 1) dist_map_mask(h, mask, want, &pmask, &pwant);
-  const int g = grid_for(h->dim_local / 2);
+  int g = grid_for(h->dim_local / 2);
   const uint64_t base = (uint64_t)h->rank << h->n_local;
-  k_masked_norm2<<<g, kThreads, 0, h->stream>>>(h->psi, h->dim_local, base, pmask, pwant, h->d_partials);
+  // contiguous selector range inside the local index (GetQubitProbability, Measure on an unsharded register): only the
+  // selected subspace is read
+  const int first = pmask ? __builtin_ctzll(pmask) : 0;
+  const int width = __builtin_popcountll(pmask);
+  const bool contiguous = pmask != 0 && (pmask >> first) == ((1ULL << width) - 1ULL) && first + width <= h->n_local;
+  if (contiguous) {
+    const uint64_t n_sub = h->dim_local >> width;
+    g = grid_for(n_sub / 2 + 1);
+    k_subspace_norm2<<<g, kThreads, 0, h->stream>>>(h->psi, n_sub, first, width, pwant & pmask, h->d_partials);
+    h->stats.bytes_moved += 16ULL * n_sub;
+  } else {
+    k_masked_norm2<<<g, kThreads, 0, h->stream>>>(h->psi, h->dim_local, base, pmask, pwant, h->d_partials);
+    h->stats.bytes_moved += 16ULL * h->dim_local;
+  }
   k_final_sum<<<1, kThreads, 0, h->stream>>>(h->d_partials, g, 1, h->d_scalars);
   CUDA_TRY(cudaGetLastError());
   h->stats.kernel_launches += 2;
   h->stats.state_passes += 1;
-  h->stats.bytes_moved += 16ULL * h->dim_local;
   double* stage = (double*)h->h_pinned;
   CUDA_TRY(cudaMemcpyAsync(stage, h->d_scalars, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   QCSIM_TRY(engine_wait(h));

@@ -244,11 +244,14 @@ __global__ void __launch_bounds__(kThreads)
 k_collapse(amp* __restrict__ psi, uint64_t n, uint64_t base, uint64_t mask, uint64_t want, double f) {
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const double g = (((base + i) & mask) == want) ? f : 0.0;
-    amp a = psi[i];
-    a.x *= g;
-    a.y *= g;
-    psi[i] = a;
+    if (((base + i) & mask) == want) {  // kept: read, scale, write
+      amp a = psi[i];
+      a.x *= f;
+      a.y *= f;
+      psi[i] = a;
+    } else {
+      psi[i] = make_amp(0.0, 0.0);  // dropped: written without being read (16 B instead of 32 B per amplitude)
+    }
   }
 }
 

@@ -82,6 +82,30 @@ k_masked_norm2(const amp* __restrict__ psi, uint64_t n, uint64_t base, uint64_t 
   if (threadIdx.x == 0) partials[blockIdx.x] = s;
 }
 
+// the same sum over a CONTIGUOUS range of selector bits [first, first + width) fixed to `want` (already shifted into
+// place), visiting only the 2^(n_bits - width) amplitudes of that subspace: GetQubitProbability reads half of the
+// state (8 B per amplitude of the state, its algorithmic figure), the collapse norm of Measure 2^-width of it
+static __global__ void __launch_bounds__(kThreads)
+k_subspace_norm2(const amp* __restrict__ psi, uint64_t n_sub, int first, int width, uint64_t want, double* __restrict__ partials) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t low = (1ULL << first) - 1ULL;
+  double acc0 = 0, acc1 = 0;
+  uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; w + stride < n_sub; w += 2 * stride) {
+    const uint64_t w1 = w + stride;
+    const amp a = psi[((w >> first) << (first + width)) | want | (w & low)];
+    const amp b = psi[((w1 >> first) << (first + width)) | want | (w1 & low)];
+    acc0 += a.x * a.x + a.y * a.y;
+    acc1 += b.x * b.x + b.y * b.y;
+  }
+  if (w < n_sub) {
+    const amp a = psi[((w >> first) << (first + width)) | want | (w & low)];
+    acc0 += a.x * a.x + a.y * a.y;
+  }
+  const double s = block_sum(acc0 + acc1);
+  if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
+
 // conj(a) . b partials (stateFidelity / ExpectationValue, QubitRegister.h:527-534, 646-660)
 static __global__ void __launch_bounds__(kThreads)
 k_inner_product(const amp* __restrict__ a, const amp* __restrict__ b, uint64_t n, double* __restrict__ partials) {
