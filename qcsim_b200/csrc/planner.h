@@ -140,6 +140,8 @@ struct RoundPlan {
   std::vector<int> vq;     // variant qubits (register qubit numbers), <= 3
   int item_bit[9];         // tile-local bit walked by item-index bit j (first k - 3 entries valid)
   std::vector<int> ops;    // indices into the op list, program order
+  bool chain_next = false; // (swizzle_kind 2) the next round uses the same warp-index bits and none of them is a register
+                           // bit of either round: every warp keeps working on its own amplitudes, no group barrier needed
 };
 
 // swizzle_kind selects the shared-memory slot swizzle the low item bits must dodge: 0 = swz() of
@@ -155,6 +157,7 @@ inline std::vector<RoundPlan> schedule_rounds(const std::vector<Op>& all, const 
 
   std::vector<int> remaining = plan.ops;
   std::vector<RoundPlan> rounds;
+  std::vector<uint32_t> used_of, vtile_of;  // per round: register bits / in-tile variant bits (tile-local masks)
   while (!remaining.empty()) {
     // Greedy fill from a seed: the seed's targets become register bits first, then ops are taken in
     // program order.  Several seeds are tried (the first pending op, and the next few ops that
@@ -229,11 +232,20 @@ inline std::vector<RoundPlan> schedule_rounds(const std::vector<Op>& all, const 
       }
     for (int q = 0; q < 64; ++q)
       if ((V >> q) & 1ULL) rp.vq.push_back(q);
-    // item-index bits.  Variant qubits inside the tile go to the warp-index part of the item index
-    // (bits 5..7: warp-uniform matrix choice; bit 8 pairs the two items a thread processes with one
-    // set of matrix loads, so it must not select the matrix); the low three item bits get distinct
-    // (position mod 3) so a quarter-warp's 128-bit shared-memory accesses land in 8 distinct bank
-    // groups under swz().
+    used_of.push_back(used);
+    uint32_t vt = 0;
+    for (int lb = 0; lb < k; ++lb)
+      if (!((used >> lb) & 1u) && ((V >> plan.tile[lb]) & 1ULL)) vt |= 1u << lb;
+    vtile_of.push_back(vt);
+    rounds.push_back(rp);
+    remaining.swap(left);
+  }
+
+  // item-index bits.  Variant qubits inside the tile go to the warp-index part of the item index
+  // (bits 5..7: warp-uniform matrix choice; bit 8 pairs the two items a thread of k_tile_pass processes with
+  // one set of matrix loads, so it must not select the matrix); the low item bits are chosen against the
+  // shared-memory swizzle (see below).  forced_warp != 0: exactly these three tile bits are the warp bits.
+  auto assign_items = [&](RoundPlan& rp, uint32_t used, uint32_t vt, uint32_t forced_warp) {
     const int ni = k - 3;
     int order[16];
     for (int j = 0; j < 16; ++j) order[j] = -1;
@@ -241,7 +253,7 @@ inline std::vector<RoundPlan> schedule_rounds(const std::vector<Op>& all, const 
     std::vector<int> rest;
     for (int lb = 0; lb < k; ++lb) {
       if ((used >> lb) & 1u) continue;
-      if ((V >> plan.tile[lb]) & 1ULL) order[top--] = lb;
+      if (forced_warp ? ((forced_warp >> lb) & 1u) : ((vt >> lb) & 1u)) order[top--] = lb;
       else rest.push_back(lb);
     }
     int pos = 0;
@@ -306,8 +318,40 @@ inline std::vector<RoundPlan> schedule_rounds(const std::vector<Op>& all, const 
     for (int lb : rest)
       if (lb >= 0) order[next_free()] = lb;
     for (int j = 0; j < 9; ++j) rp.item_bit[j] = (j < ni && order[j] >= 0) ? order[j] : 0;
-    rounds.push_back(rp);
-    remaining.swap(left);
+  };
+
+  const int n_rounds = (int)rounds.size();
+  if (swizzle_kind == 2 && k - 3 == 8) {
+    // Chains of rounds that share their three warp-index bits: the bits are register bits of none of the rounds and
+    // contain every round's in-tile variant bits, so a warp reads and writes the same 256 amplitudes round after
+    // round -- the rounds of a chain are separated by __syncwarp() instead of the group barrier.
+    const uint32_t all_bits = (1u << k) - 1u;
+    int i = 0;
+    while (i < n_rounds) {
+      uint32_t F = all_bits & ~used_of[i], Nd = vtile_of[i];
+      int j = i + 1;
+      while (j < n_rounds) {
+        const uint32_t F2 = F & ~used_of[j], N2 = Nd | vtile_of[j];
+        if (__builtin_popcount(N2) > 3 || (N2 & ~F2) != 0 || __builtin_popcount(F2) < 3) break;
+        F = F2;
+        Nd = N2;
+        ++j;
+      }
+      if (j - i >= 2) {
+        uint32_t W = Nd;
+        for (int lb = k - 1; lb >= 0 && __builtin_popcount(W) < 3; --lb)  // high slot bits first: the low ones serve the lanes
+          if (((F >> lb) & 1u) && !((W >> lb) & 1u)) W |= 1u << lb;
+        for (int r = i; r < j; ++r) {
+          assign_items(rounds[r], used_of[r], vtile_of[r], W);
+          rounds[r].chain_next = r + 1 < j;
+        }
+      } else {
+        assign_items(rounds[i], used_of[i], vtile_of[i], 0);
+      }
+      i = j;
+    }
+  } else {
+    for (int r = 0; r < n_rounds; ++r) assign_items(rounds[r], used_of[r], vtile_of[r], 0);
   }
   return rounds;
 }
@@ -485,7 +529,7 @@ inline void build_round_matrices(const std::vector<Op>& all, const PassPlan& pla
 struct RoundDescHost {
   uint32_t rb;       // rb0 | rb1 << 8 | rb2 << 16 : tile bit held by register bit j
   uint32_t tb[3];    // tile bit walked by item-index bit j, one byte each
-  uint32_t var;      // nvar | (src | pos << 1) << (8 + 8 j): src 0 = tile bit, 1 = index bit outside the tile
+  uint32_t var;      // nvar | chain flag << 7 | (src | pos << 1) << (8 + 8 j): src 0 = tile bit, 1 = index bit outside the tile
   uint32_t mat_off;  // first matrix of the round
 };
 
@@ -496,7 +540,7 @@ inline RoundDescHost make_round_desc(const RoundPlan& rp, const int* local_of, u
   for (int w = 0; w < 3; ++w) rd.tb[w] = 0;
   for (int j = 0; j < 9; ++j) rd.tb[j >> 2] |= (uint32_t)rp.item_bit[j] << (8 * (j & 3));
   const int nv = (int)rp.vq.size();
-  rd.var = (uint32_t)nv;
+  rd.var = (uint32_t)nv | (rp.chain_next ? 0x80u : 0u);  // bit 7: the next round needs no group barrier (same warp bits)
   for (int j = 0; j < nv; ++j) {
     const int q = rp.vq[j];
     const uint32_t e = local_of[q] >= 0 ? (uint32_t)(local_of[q] << 1) : (uint32_t)((q << 1) | 1);

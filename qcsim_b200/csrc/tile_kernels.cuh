@@ -179,7 +179,7 @@ static __global__ void __launch_bounds__(kTileThreads, 2) k_tile_pass(amp* __res
     for (int r = 0; r < A.n_rounds; ++r) {
       const TileRoundDesc rd = A.rounds[r];
       const uint32_t so0 = swz(1u << (rd.rb & 31u)), so1 = swz(1u << ((rd.rb >> 8) & 31u)), so2 = swz(1u << ((rd.rb >> 16) & 31u));
-      const int nvar = rd.var & 0xff;
+      const int nvar = rd.var & 0x7f;
       const uint32_t n_var = 1u << nvar;
       const uint32_t pair_off = swz(1u << ((rd.tb[2]) & 31u));  // item bit 8 -> tile bit (only used when items > 256)
 #pragma unroll 1

@@ -235,6 +235,8 @@ __device__ __forceinline__ void producer(const PipeGeom& G, const Smem& m) {
 struct RoundTable {
   uint32_t load_g[8], store_g[8], load_t[4], store_t[4], warp_hi[8], warp_ms[8];
   uint32_t x_hi, x_i0, x_p0, x_p1;
+  uint32_t chain_next;  // the next round keeps every warp on its own amplitudes: __syncwarp() instead of the group barrier
+  uint32_t pad[3];
 };
 
 // Dynamic shared memory (1024 B aligned): 6 tile buffers | round matrices | mbarriers | round tables.
@@ -304,7 +306,7 @@ static __global__ void __launch_bounds__(kPipeThreads, 1) k_tile_pipe(const __gr
       const uint32_t w = j - 24;
       uint32_t hi = 0;
       for (int q = 0; q < 3; ++q) hi |= ((w >> q) & 1u) ? ib(5 + q) : 0u;
-      const int nvar = rd.var & 0xff;
+      const int nvar = rd.var & 0x7f;
       uint32_t vidx = 0, gs = 0;
       for (int q = 0; q < kMaxVariantBits; ++q) {
         const uint32_t en = (rd.var >> (8 + 8 * q)) & 0xffu;
@@ -320,6 +322,7 @@ static __global__ void __launch_bounds__(kPipeThreads, 1) k_tile_pipe(const __gr
       rt[r].x_i0 = tswz(ib(0));
       rt[r].x_p0 = tswz(ib(3));
       rt[r].x_p1 = tswz(ib(4));
+      rt[r].chain_next = (rd.var >> 7) & 1u;
     }
   }
   asm volatile("bar.sync 3, %0;" ::"n"(kPipeConsumers) : "memory");  // all consumers (the producer is already moving tiles)
@@ -391,7 +394,8 @@ static __global__ void __launch_bounds__(kPipeThreads, 1) k_tile_pipe(const __gr
           tdw[2 * (a0 ^ x_i0) + (sq ^ 1u)] = c_second[p][1];
         }
         if (r + 1 == A.n_rounds) fence_proxy_async();
-        group_bar(group);
+        if (T.chain_next && r + 1 < A.n_rounds) __syncwarp();
+        else group_bar(group);
       }
     }
     if (A.n_rounds == 0) {

@@ -227,3 +227,90 @@ int hl_pipe_pass(const qcsim_gate* gates, int count, unsigned long long tile_mas
   return (int)rounds.size();
 }
 }
+
+// ---- what fusion_execute_local would launch (fusion.cu), counted without a GPU --------------------------------
+extern "C" {
+// out = {fused launches, rounds, ops run as single-gate kernels, fused passes before launch splitting, matrices}
+void hl_fusion_stats(const qcsim_gate* gates, int count, int n_local, int K, int L, int max_rounds, int max_mats, int swizzle_kind, int* out) {
+  std::vector<Op> ops;
+  for (int i = 0; i < count; ++i) ops.push_back(classify(gates[i].nq, gates[i].m, gates[i].flags, gates[i].q, gates[i].c1, gates[i].c2));
+  const std::vector<PlanStep> steps = plan_passes(ops, n_local, K, L, 1 << 20, 1 << 30);
+  int launches = 0, rounds = 0, singles = 0, passes = 0, mats = 0;
+  for (const PlanStep& st : steps) {
+    if (!st.fused) {
+      ++singles;
+      continue;
+    }
+    const std::vector<RoundPlan> rplan = schedule_rounds(ops, st.pass, 3, swizzle_kind);
+    size_t n_mats = 0;
+    for (const RoundPlan& rp : rplan) n_mats += (size_t)1 << rp.vq.size();
+    // launch splitting as in launch_pass_pipe
+    int l = 0;
+    size_t r = 0;
+    while (r < rplan.size()) {
+      int nr = 0;
+      size_t mi = 0;
+      while (r < rplan.size() && nr < max_rounds && mi + ((size_t)1 << rplan[r].vq.size()) <= (size_t)max_mats) {
+        mi += (size_t)1 << rplan[r].vq.size();
+        ++nr;
+        ++r;
+      }
+      ++l;
+    }
+    const double cost_fused = std::max(32.0 * l, 24.0 * rplan.size());
+    double cost_alone = 0;
+    for (int idx : st.pass.ops) cost_alone += standalone_cost(ops[idx]);
+    if (cost_fused >= cost_alone) {
+      singles += (int)st.pass.ops.size();
+      continue;
+    }
+    ++passes;
+    launches += l;
+    rounds += (int)rplan.size();
+    mats += (int)n_mats;
+  }
+  out[0] = launches;
+  out[1] = rounds;
+  out[2] = singles;
+  out[3] = passes;
+  out[4] = mats;
+}
+}
+
+// ---- bank-conflict census of the DMMA fragment accesses for a whole gate list (what launch_pass_pipe would run) ----
+extern "C" {
+// hist[d] = number of (round, access kind) pairs whose half-warp conflict degree is d (d = 1, 2, 4, 8); returns rounds
+int hl_pipe_conflicts(const qcsim_gate* gates, int count, int n_local, int* hist, int* chained) {
+  std::vector<Op> ops;
+  for (int i = 0; i < count; ++i) ops.push_back(classify(gates[i].nq, gates[i].m, gates[i].flags, gates[i].q, gates[i].c1, gates[i].c2));
+  const std::vector<PlanStep> steps = plan_passes(ops, n_local, 11, 3, 1 << 20, 1 << 30);
+  for (int d = 0; d < 16; ++d) hist[d] = 0;
+  int rounds = 0;
+  *chained = 0;
+  auto bank = [](uint32_t s) { return (s ^ (s >> 3)) & 7u; };
+  for (const PlanStep& st : steps) {
+    if (!st.fused || (int)st.pass.tile.size() != 11) continue;
+    TmaTileGeom g;
+    if (!tma_tile_geometry(st.pass.tile, n_local, &g)) continue;
+    PassPlan plan = st.pass;
+    for (int j = 0; j < 11; ++j) plan.tile[j] = g.slot_qubit[j];
+    const std::vector<RoundPlan> rplan = schedule_rounds(ops, plan, 3, 2);
+    for (const RoundPlan& rp : rplan) {
+      ++rounds;
+      if (rp.chain_next) ++*chained;
+      const uint32_t r0 = 1u << rp.rbits[0], r1 = 1u << rp.rbits[1], i0 = 1u << rp.item_bit[0], i1 = 1u << rp.item_bit[1], i2 = 1u << rp.item_bit[2];
+      for (int kind = 0; kind < 2; ++kind) {
+        int cnt[16] = {0}, worst = 0;
+        for (int lane = 0; lane < 16; ++lane) {
+          const uint32_t s = kind == 0 ? (((lane & 1) ? r0 : 0u) ^ ((lane & 2) ? r1 : 0u) ^ ((lane & 4) ? i0 : 0u) ^ ((lane & 8) ? i1 : 0u))
+                                       : (((lane & 1) ? i1 : 0u) ^ ((lane & 2) ? i2 : 0u) ^ ((lane & 4) ? r0 : 0u) ^ ((lane & 8) ? r1 : 0u));
+          const int half = kind == 0 ? (lane & 1) : ((lane >> 2) & 1);
+          worst = std::max(worst, ++cnt[2 * bank(s) + half]);
+        }
+        hist[worst]++;
+      }
+    }
+  }
+  return rounds;
+}
+}

@@ -23,7 +23,10 @@ fi
 if [ "$N" = 8 ]; then
   run bench8_qft36 $TR bench.py --gpus 8 --steps 3 --warmup 3 --workload qft --qubits 33
   run bench8_random36 $TR bench.py --gpus 8 --steps 10 --warmup 3 --qubits 33
-  # QCSim's own GroverAlgorithm.h on the C++ drop-in class, 31 qubits, eight GPUs of one process
-  ( time QCSIM_B200_FUSION=1 QCSIM_B200_DEVICES=0,1,2,3,4,5,6,7 timeout 600 tests/cpp/facade_test.bin grover_ranges 16 46757 $O/facade_g31_8.bin ) 2>&1 | grep -v "^$" | tr '\n' ' ' | tee $O/${R}_facade_grover31_8gpu.log; echo
+fi
+if [ "$N" -ge 4 ]; then
+  # QCSim's own GroverAlgorithm.h on the C++ drop-in class, 31 qubits, N GPUs of one process
+  DEVS=$(seq -s, 0 $((N-1)))
+  ( time QCSIM_B200_FUSION=1 QCSIM_B200_DEVICES=$DEVS timeout 600 tests/cpp/facade_test.bin grover_ranges 16 46757 $O/facade_g31_$N.bin ) 2>&1 | grep -v "^$" | tr '\n' ' ' | tee $O/${R}_facade_grover31_${N}gpu.log; echo
 fi
 python tools/compare_grover.py | tee $O/${R}_grover_compare${N}.log
