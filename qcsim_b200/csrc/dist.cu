@@ -728,7 +728,7 @@ int dist_chained_walk(qcsim_sv* h) {
   for (int r = 0; r < h->world; ++r) {
     double out = 0.0;
     if (r == h->rank) {
-      k_sequential_walk<<<1, kThreads, 0, h->stream>>>(h->psi, h->dim_local, h->n_chunks, h->d_prefix_hi, h->d_chunk_K, h->d_chunk_flags, acc,
+      k_sequential_walk<<<1, kWalkThreads, 0, h->stream>>>(h->psi, h->dim_local, h->n_chunks, h->d_prefix_hi, h->d_chunk_K, h->d_chunk_flags, acc,
                                                        h->d_acc_start, nullptr);
       CUDA_TRY(cudaGetLastError());
       h->stats.kernel_launches += 1;

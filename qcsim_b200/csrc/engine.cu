@@ -875,7 +875,7 @@ int engine_resolve_draws(qcsim_sv* h, const double* probs, uint64_t count, uint6
   if (h->world > 1) {
     QCSIM_TRY(dist_chained_walk(h));  // rank by rank: walk with the predecessor's final sum
   } else {
-    k_sequential_walk<<<1, kThreads, 0, h->stream>>>(h->psi, h->dim_local, h->n_chunks, h->d_prefix_hi, h->d_chunk_K, h->d_chunk_flags, start,
+    k_sequential_walk<<<1, kWalkThreads, 0, h->stream>>>(h->psi, h->dim_local, h->n_chunks, h->d_prefix_hi, h->d_chunk_K, h->d_chunk_flags, start,
                                                      h->d_acc_start, nullptr);
     CUDA_TRY(cudaGetLastError());
     h->stats.kernel_launches += 1;

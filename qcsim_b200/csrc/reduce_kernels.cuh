@@ -160,9 +160,10 @@ k_chunk_sums(const amp* __restrict__ psi, uint64_t n, uint64_t n_chunks, dd* __r
 // falls exactly on a half (round-half-even then depends on the running parity).  So
 //   1. k_chunk_sums        exact (double-double) mass per chunk of 4096 amplitudes -> the binade each chunk starts in
 //   2. k_chunk_increments  per chunk: K = sum rint(p_i / u) as an exact integer, flags for ties / overflow
-//   3. k_sequential_walk   ONE thread walks the chunks: acc += u K when the chunk stays inside its predicted binade
-//                          and had no tie, else it replays the chunk's 4096 additions one by one (a power-of-two
-//                          crossing happens at most ~once per binade, ties are rare): acc at every chunk start, exact
+//   3. k_sequential_walk   one block walks the chunks: a run of chunks inside the binade of the running sum is an
+//                          integer prefix sum of their K (1024 chunks per step); the chunk that ends a run (tie, or
+//                          the sum crosses a power of two: ~once per binade) has its 4096 additions replayed one by
+//                          one: acc at every chunk start, exact
 //   4. k_resolve_draws     per draw: binary search over the chunk starts, then the reference's own loop inside one chunk.
 // Cost: two passes over the state + O(chunks) sequential work, for any number of draws.
 static constexpr unsigned long long kNoOutcome = ~0ULL;
@@ -253,84 +254,107 @@ k_chunk_increments(const amp* __restrict__ psi, uint64_t n, uint64_t n_chunks, c
   }
 }
 
-// One block; thread 0 carries the sum, the others stage chunk records.  acc_start[c] = the reference's running sum
-// before element c * 4096 (acc_start[n_chunks] = after the last element), starting from `start` (the sum the lower
-// ranks ended with on a sharded register).
-static __global__ void __launch_bounds__(kThreads)
+// One block.  acc_start[c] = the reference's running sum before element c * 4096 (acc_start[n_chunks] = after the
+// last element), starting from `start` (the sum the lower ranks ended with on a sharded register).
+// A run of chunks that stays inside the binade of the running sum is resolved by the whole block at once: with
+// e0 = ilogb(carry), every chunk whose predicted binade is e0 has its K in units of u = 2^(e0-52), so the sum before
+// chunk j of the run is  carry + u * (K_0 + ... + K_{j-1})  exactly (an integer prefix sum), as long as that value is
+// still below 2^(e0+1).  The first chunk that breaks the run -- tie / overflow flag, a predicted binade other than
+// e0, or a sum that leaves the binade -- is replayed element by element by thread 0 and the next run starts behind it.
+constexpr int kWalkThreads = 1024;
+static __global__ void __launch_bounds__(kWalkThreads)
 k_sequential_walk(const amp* __restrict__ psi, uint64_t n, uint64_t n_chunks, const double* __restrict__ prefix_hi,
                   const unsigned long long* __restrict__ K, const int* __restrict__ flags, double start, double* __restrict__ acc_start,
                   unsigned long long* __restrict__ n_slow_out) {
-  constexpr int TILE = 512;
-  __shared__ unsigned long long sK[TILE];
-  __shared__ int sF[TILE];
-  __shared__ int sE[TILE];
-  __shared__ double sOut[TILE];
+  __shared__ unsigned long long warp_tot[32];
+  __shared__ int warp_first[32];
   __shared__ double sP[kChunk];
-  __shared__ double carry;
-  __shared__ int want_chunk;
+  __shared__ double carry_s;
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5, n_warps = blockDim.x >> 5;
+  constexpr unsigned long long kClamp = 1ULL << 53;  // a chunk this heavy leaves any binade; clamping keeps the prefix sum inside 64 bits
   unsigned long long n_slow = 0;
-  if (threadIdx.x == 0) carry = start;
-  __syncthreads();
-  for (uint64_t c0 = 0; c0 < n_chunks; c0 += TILE) {
-    const int cnt = (int)((n_chunks - c0 < (uint64_t)TILE) ? (n_chunks - c0) : (uint64_t)TILE);
-    for (int j = threadIdx.x; j < cnt; j += blockDim.x) {
-      sK[j] = K[c0 + j];
-      sF[j] = flags[c0 + j];
-      const double ph = prefix_hi[c0 + j];
-      sE[j] = ph > 0.0 ? ilogb(ph) : -5000;
+  double carry = start;  // uniform across the block
+  uint64_t c = 0;
+  while (c < n_chunks) {
+    const int cnt = (int)((n_chunks - c < (uint64_t)blockDim.x) ? (n_chunks - c) : (uint64_t)blockDim.x);
+    const bool have = t < cnt;
+    const int e0 = carry > 0.0 ? ilogb(carry) : -6000;  // -6000: no binade yet, the first non-zero chunk is replayed
+    int f = kChunkZero, e = -5000;
+    unsigned long long inc = 0;
+    if (have) {
+      f = flags[c + t];
+      const double ph = prefix_hi[c + t];
+      e = ph > 0.0 ? ilogb(ph) : -5000;
+      if (!(f & kChunkZero)) {
+        const unsigned long long k = K[c + t];
+        inc = k < kClamp ? k : kClamp;
+      }
+    }
+    const bool moves = have && !(f & kChunkZero);
+    bool fails = moves && ((f & kChunkSlow) || e != e0);
+    // inclusive prefix sum of the increments over the block
+    unsigned long long incl = inc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      const unsigned long long mine = lane < n_warps ? warp_tot[lane] : 0ULL;
+      unsigned long long run = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long v = __shfl_up_sync(0xffffffffu, run, o);
+        if (lane >= o) run += v;
+      }
+      warp_tot[lane] = run - mine;  // exclusive
     }
     __syncthreads();
-    int j = 0;
-    while (j < cnt) {  // uniform loop: thread 0 advances until it needs a chunk replayed
-      if (threadIdx.x == 0) {
-        double acc = carry;
-        int jj = j;
-        want_chunk = -1;
-        for (; jj < cnt; ++jj) {
-          sOut[jj] = acc;
-          const int f = sF[jj];
-          if (f & kChunkZero) continue;
-          bool fast = !(f & kChunkSlow) && acc > 0.0 && ilogb(acc) == sE[jj];
-          if (fast) {
-            const double nxt = acc + scalbn((double)sK[jj], sE[jj] - 52);  // exact while it stays inside the binade
-            if (ilogb(nxt) == sE[jj]) {
-              acc = nxt;
-              continue;
-            }
-          }
-          want_chunk = jj;  // replay this chunk element by element
-          break;
-        }
-        carry = acc;
-        if (want_chunk < 0) want_chunk = -1 - cnt;  // encoded: tile finished
-      }
-      __syncthreads();
-      const int w = want_chunk;
-      if (w < 0) {
-        j = cnt;
-        __syncthreads();
-        break;
-      }
-      // cooperative load of chunk w's probabilities, then thread 0 adds them in order
-      const uint64_t lo = (c0 + (uint64_t)w) << kChunkLog2;
-      for (int k2 = threadIdx.x; k2 < (int)kChunk; k2 += blockDim.x) {
+    incl += warp_tot[wid];
+    // (double)incl is exact below 2^53; above, the sum is outside the binade whatever the rounding
+    const double before = carry + scalbn((double)(incl - inc), e0 - 52);
+    const double after = carry + scalbn((double)incl, e0 - 52);
+    if (moves && !fails && ilogb(after) != e0) fails = true;
+    // first chunk of the tile that breaks the run
+    const unsigned ballot = __ballot_sync(0xffffffffu, fails);
+    if (lane == 0) warp_first[wid] = ballot ? (wid * 32 + __ffs((int)ballot) - 1) : (1 << 30);
+    __syncthreads();
+    if (wid == 0) {
+      int v = lane < n_warps ? warp_first[lane] : (1 << 30);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+      if (lane == 0) warp_first[0] = v;
+    }
+    __syncthreads();
+    const int first = warp_first[0] < cnt ? warp_first[0] : cnt;  // chunks [0, first) of the tile are resolved
+    if (have && t <= first) acc_start[c + t] = before;             // (t == first: the replayed chunk starts here)
+    if (first < cnt) {
+      if (t == first) carry_s = before;
+      // cooperative load of the chunk's probabilities, then thread 0 adds them in order like the reference
+      const uint64_t lo = (c + (uint64_t)first) << kChunkLog2;
+      for (int k2 = t; k2 < (int)kChunk; k2 += blockDim.x) {
         const uint64_t i = lo + k2;
         sP[k2] = (i < n) ? norm_rn(psi[i]) : 0.0;
       }
       __syncthreads();
-      if (threadIdx.x == 0) {
-        double acc = carry;
+      if (t == 0) {
+        double acc = carry_s;
         for (int k2 = 0; k2 < (int)kChunk; ++k2) acc = __dadd_rn(acc, sP[k2]);
-        carry = acc;
-        ++n_slow;
+        carry_s = acc;
       }
-      j = w + 1;
-      __syncthreads();
+      ++n_slow;
+      c += (uint64_t)first + 1;
+    } else {
+      if (t == cnt - 1) carry_s = after;
+      c += (uint64_t)cnt;
     }
-    for (int jj = threadIdx.x; jj < cnt; jj += blockDim.x) acc_start[c0 + jj] = sOut[jj];
     __syncthreads();
+    carry = carry_s;
+    __syncthreads();  // carry_s, warp_tot and warp_first are rewritten by the next tile
   }
-  if (threadIdx.x == 0) {
+  if (t == 0) {
     acc_start[n_chunks] = carry;
     if (n_slow_out) *n_slow_out = n_slow;
   }

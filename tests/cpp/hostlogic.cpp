@@ -313,4 +313,38 @@ int hl_pipe_conflicts(const qcsim_gate* gates, int count, int n_local, int* hist
   }
   return rounds;
 }
+// Diagnostic dump of every DMMA round of the TMA pipeline plan (slot order, register / item bits, conflict degrees).
+void hl_pipe_round_dump(const qcsim_gate* gates, int count, int n_local) {
+  std::vector<Op> ops;
+  for (int i = 0; i < count; ++i) ops.push_back(classify(gates[i].nq, gates[i].m, gates[i].flags, gates[i].q, gates[i].c1, gates[i].c2));
+  const std::vector<PlanStep> steps = plan_passes(ops, n_local, 11, 3, 1 << 20, 1 << 30);
+  auto bank = [](uint32_t s) { return (s ^ (s >> 3)) & 7u; };
+  for (const PlanStep& st : steps) {
+    if (!st.fused || (int)st.pass.tile.size() != 11) continue;
+    TmaTileGeom g;
+    if (!tma_tile_geometry(st.pass.tile, n_local, &g)) continue;
+    PassPlan plan = st.pass;
+    for (int j = 0; j < 11; ++j) plan.tile[j] = g.slot_qubit[j];
+    const std::vector<RoundPlan> rplan = schedule_rounds(ops, plan, 3, 2);
+    printf("pass slots:");
+    for (int j = 0; j < 11; ++j) printf(" %d", g.slot_qubit[j]);
+    printf("  (boxed 2^%d, enum %d)\n", g.box_log2, g.n_enum);
+    for (const RoundPlan& rp : rplan) {
+      const uint32_t r0 = 1u << rp.rbits[0], r1 = 1u << rp.rbits[1], i0 = 1u << rp.item_bit[0], i1 = 1u << rp.item_bit[1], i2 = 1u << rp.item_bit[2];
+      int deg[2];
+      for (int kind = 0; kind < 2; ++kind) {
+        int cnt[16] = {0}, worst = 0;
+        for (int lane = 0; lane < 16; ++lane) {
+          const uint32_t s = kind == 0 ? (((lane & 1) ? r0 : 0u) ^ ((lane & 2) ? r1 : 0u) ^ ((lane & 4) ? i0 : 0u) ^ ((lane & 8) ? i1 : 0u))
+                                       : (((lane & 1) ? i1 : 0u) ^ ((lane & 2) ? i2 : 0u) ^ ((lane & 4) ? r0 : 0u) ^ ((lane & 8) ? r1 : 0u));
+          const int half = kind == 0 ? (lane & 1) : ((lane >> 2) & 1);
+          worst = std::max(worst, ++cnt[2 * bank(s) + half]);
+        }
+        deg[kind] = worst;
+      }
+      printf("   round r=(%d,%d,%d) items=(%d,%d,%d | %d %d %d %d %d) nvar=%d chain=%d  load x%d store x%d\n", rp.rbits[0], rp.rbits[1], rp.rbits[2], rp.item_bit[0],
+             rp.item_bit[1], rp.item_bit[2], rp.item_bit[3], rp.item_bit[4], rp.item_bit[5], rp.item_bit[6], rp.item_bit[7], (int)rp.vq.size(), (int)rp.chain_next, deg[0], deg[1]);
+    }
+  }
+}
 }

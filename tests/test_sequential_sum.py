@@ -15,38 +15,60 @@ import pytest
 CHUNK = 64  # the device uses 4096; a small chunk makes crossings and ties frequent here
 
 
+TILE = 8    # chunks resolved per step of the walk (the device: 1024)
+
+
+def ilogb(x):
+    return math.frexp(x)[1] - 1
+
+
 def walk(p, start=0.0):
     """acc at every chunk start (+ final) computed the way the device does it; returns (acc_start, n_replayed)"""
     n_chunks = (len(p) + CHUNK - 1) // CHUNK
     # 1. exact chunk masses -> predicted binade of every chunk start (math.fsum = exact, like the double-double prefix)
     prefix = [math.fsum([start] + list(p[: c * CHUNK])) for c in range(n_chunks)]
-    acc_start = np.zeros(n_chunks + 1)
-    acc = start
-    replayed = 0
+    # 2. k_chunk_increments: K in units of the predicted binade's ulp, flags
+    K, slow, zero, E = [], [], [], []
     for c in range(n_chunks):
-        acc_start[c] = acc
         chunk = p[c * CHUNK: (c + 1) * CHUNK]
-        if not np.any(chunk):
-            continue
-        e = math.frexp(prefix[c])[1] - 1 if prefix[c] > 0 else -5000
-        slow = e <= -900
-        K = 0
-        if not slow:
+        e = ilogb(prefix[c]) if prefix[c] > 0 else -5000
+        s, k = e <= -900, 0
+        if not s:
             x = np.ldexp(chunk, 52 - e)                      # exact scaling
             if np.any(x >= 2.0 ** 52) or np.any(x - np.floor(x) == 0.5):
-                slow = True
+                s = True
             else:
-                K = int(np.sum(np.rint(x).astype(np.uint64), dtype=np.uint64))
-        fast = (not slow) and acc > 0 and (math.frexp(acc)[1] - 1) == e
-        if fast:
-            nxt = acc + math.ldexp(float(K), e - 52)
-            if math.frexp(nxt)[1] - 1 == e:
-                acc = nxt
-                continue
-        replayed += 1
-        for v in chunk:
-            acc = acc + float(v)
-    acc_start[n_chunks] = acc
+                k = int(np.sum(np.rint(x).astype(np.uint64), dtype=np.uint64))
+        K.append(min(k, 1 << 53)); slow.append(s); zero.append(not np.any(chunk)); E.append(e)
+    # 3. k_sequential_walk: runs of chunks inside the binade of the running sum are an integer prefix sum
+    acc_start = np.zeros(n_chunks + 1)
+    carry, c, replayed = start, 0, 0
+    while c < n_chunks:
+        cnt = min(TILE, n_chunks - c)
+        e0 = ilogb(carry) if carry > 0 else -6000
+        incl, first = 0, cnt
+        before, after = [], []
+        for t in range(cnt):
+            inc = 0 if zero[c + t] else K[c + t]
+            before.append(carry + math.ldexp(float(incl), e0 - 52))
+            incl += inc
+            after.append(carry + math.ldexp(float(incl), e0 - 52))
+            fails = (not zero[c + t]) and (slow[c + t] or E[c + t] != e0 or ilogb(after[t]) != e0)
+            if fails and first == cnt:
+                first = t
+        for t in range(min(first + 1, cnt)):
+            acc_start[c + t] = before[t]
+        if first < cnt:
+            acc = before[first]
+            for v in p[(c + first) * CHUNK: (c + first + 1) * CHUNK]:
+                acc = acc + float(v)
+            carry = acc
+            replayed += 1
+            c += first + 1
+        else:
+            carry = after[cnt - 1]
+            c += cnt
+    acc_start[n_chunks] = carry
     return acc_start, replayed
 
 
