@@ -101,16 +101,26 @@ static int launch_pass_pipe(qcsim_sv* h, const std::vector<Op>& all, const PassP
   if ((int)plan_in.tile.size() != kPipeTileBits || !tma_tile_geometry(plan_in.tile, h->n_local, &g)) return QCSIM_ERR_UNSUPPORTED;
   if (!tensor_map_encoder()) return QCSIM_ERR_UNSUPPORTED;
   const int k = kPipeTileBits;
-  // the tile in shared-memory slot order: everything downstream (round bits, item bits, variants) is in slot bits
+  // Tensor-dimension order = shared-memory slot order of the boxed qubits, chosen for the fewest bank conflicts of
+  // this pass's DMMA rounds (planner.h); everything downstream (round bits, item bits, variants) is in slot bits.
+  static const int layout_search = env_int("QCSIM_PIPE_LAYOUT", 1), always_chain = env_int("QCSIM_PIPE_CHAIN", 0);
+  static thread_local PipePassArgs A;  // ~30 KiB: keep it off the stack; the launch copies it
+  static thread_local bool reorder_rejected = false;  // the driver refused a reordered tensor map once: stay on the ascending order
   PassPlan plan = plan_in;
-  for (int j = 0; j < k; ++j) plan.tile[j] = g.slot_qubit[j];
+  std::vector<RoundPlan> rplan;
+  for (int attempt = 0;; ++attempt) {
+    TmaTileGeom chosen = g;
+    rplan = schedule_rounds_best_layout(all, plan_in, g, kMaxVariantBits, &chosen, &plan, nullptr, always_chain != 0,
+                                        layout_search != 0 && !reorder_rejected);
+    const int rc = fusion_fill_pipe_geom(h, plan_in.tile, chosen, &A.geom);
+    if (rc == QCSIM_OK) break;
+    if (attempt > 0 || reorder_rejected || !layout_search) return rc;
+    reorder_rejected = true;
+  }
   int local_of[64];
   for (int q = 0; q < 64; ++q) local_of[q] = -1;
   for (int j = 0; j < k; ++j) local_of[plan.tile[j]] = j;
-  const std::vector<RoundPlan> rplan = schedule_rounds(all, plan, kMaxVariantBits, /*swizzle_kind=*/2);
 
-  static thread_local PipePassArgs A;  // ~30 KiB: keep it off the stack; the launch copies it
-  QCSIM_TRY(fusion_fill_pipe_geom(h, plan_in.tile, g, &A.geom));
   const uint64_t grid = std::min<uint64_t>(A.geom.n_tiles, (uint64_t)kNumSMs);
   static const int debug = env_int("QCSIM_DEBUG_PLAN", 0);
 

@@ -149,7 +149,8 @@ struct RoundPlan {
 // (only slot bits 3..5 fold onto 0..2) with one item per lane, 2 = the TMA swizzle with the DMMA
 // fragment mapping of tile_pipe.cuh (register-bit order and item bits 0..2 chosen together).
 inline std::vector<RoundPlan> schedule_rounds(const std::vector<Op>& all, const PassPlan& plan, int max_variant_bits = 3,
-                                              int swizzle_kind = 0) {
+                                              int swizzle_kind = 0, int* conflict_cost = nullptr, bool always_chain = false) {
+  int total_cost = 0;  // swizzle_kind 2: sum over rounds of (load degree + store degree); 2 per round = conflict-free
   const int k = (int)plan.tile.size();
   int local_of[64];
   for (int q = 0; q < 64; ++q) local_of[q] = -1;
@@ -245,7 +246,8 @@ inline std::vector<RoundPlan> schedule_rounds(const std::vector<Op>& all, const 
   // (bits 5..7: warp-uniform matrix choice; bit 8 pairs the two items a thread of k_tile_pass processes with
   // one set of matrix loads, so it must not select the matrix); the low item bits are chosen against the
   // shared-memory swizzle (see below).  forced_warp != 0: exactly these three tile bits are the warp bits.
-  auto assign_items = [&](RoundPlan& rp, uint32_t used, uint32_t vt, uint32_t forced_warp) {
+  auto assign_items = [&](RoundPlan& rp, uint32_t used, uint32_t vt, uint32_t forced_warp) -> int {
+    int round_cost = 0;
     const int ni = k - 3;
     int order[16];
     for (int j = 0; j < 16; ++j) order[j] = -1;
@@ -269,36 +271,59 @@ inline std::vector<RoundPlan> schedule_rounds(const std::vector<Op>& all, const 
       //   result stores  : register bits 0,1 (4 rows; bit 0 also picks the half) x item bits 1,2
       // Pick the order of the three register bits and the item bits (i0,i1,i2) with the fewest conflicts under tswz
       // (only slot bits 0..5 move the bank: bank = (s ^ s >> 3) & 7).
-      auto bank = [](uint32_t s) { return (s ^ (s >> 3)) & 7u; };
-      auto degree = [&](uint32_t half_bit, uint32_t b1, uint32_t b2, uint32_t b3) {  // lanes: bit0 -> half_bit (+ half), bit1 -> b1, bit2 -> b2, bit3 -> b3
-        int cnt[16], worst = 0;
-        for (int c = 0; c < 16; ++c) cnt[c] = 0;
-        for (int lane = 0; lane < 16; ++lane) {
-          const uint32_t sidx = ((lane & 1) ? half_bit : 0u) ^ ((lane & 2) ? b1 : 0u) ^ ((lane & 4) ? b2 : 0u) ^ ((lane & 8) ? b3 : 0u);
-          worst = std::max(worst, ++cnt[2 * bank(sidx) + (lane & 1)]);
-        }
-        return worst;
-      };
-      int best_cost = 1 << 30, best_r[3] = {rp.rbits[0], rp.rbits[1], rp.rbits[2]}, best_i[3] = {-1, -1, -1};
-      const int perms[6][3] = {{0, 1, 2}, {0, 2, 1}, {1, 0, 2}, {1, 2, 0}, {2, 0, 1}, {2, 1, 0}};
+      // Under tswz only slot bits 0..5 move the bank, each by one bit: code(s) = unit vector (s mod 3) for s < 6, else 0.
+      // The 16 lanes map linearly (XOR) onto 16 columns; the half-selecting lane bit is independent of the rest, so the
+      // conflict degree is 2^(3 - rank) with rank = number of distinct non-zero codes among the other three lane bits:
+      //   loads : {r1, i0, i1}      stores : {r1, i1, i2}
+      // r1 is one of the three register bits, the items come from `rest`; only the codes matter, so the search runs
+      // over code classes (4^3 x 3 candidates) instead of slots.
+      auto code = [](int s) -> uint32_t { return s < 3 ? 1u << s : (s < 6 ? 1u << (s - 3) : 0u); };
+      auto cls = [](int s) { return s < 6 ? s % 3 : 3; };  // 3 = no bank bit
+      const uint32_t cls_code[4] = {1u, 2u, 4u, 0u};
+      std::vector<int> by_cls[4];
+      for (int lb : rest) by_cls[cls(lb)].push_back(lb);  // ascending
+      int best_cost = 1 << 30, best_r1 = 0, best_c[3] = {3, 3, 3};
       const int nrest = (int)rest.size();
-      for (const auto& pm : perms) {
-        const int r0 = rp.rbits[pm[0]], r1 = rp.rbits[pm[1]];
-        for (int a = 0; a < nrest; ++a)
-          for (int b = 0; b < nrest; ++b)
-            for (int c = 0; c < nrest; ++c) {
-              if (a == b || a == c || b == c) continue;
-              // loads: lane = 4 g + t: t bits -> (r0, r1), g bits 0,1 -> (i0, i1); stores: lane = 4 g + t: t bits -> (i1, i2), g bits 0,1 -> (r0, r1)
-              // (a half-warp of the store is lanes 0..15 = g 0..3: reorder so that bit0 is the half-selecting register bit)
-              const int cost = degree(1u << r0, 1u << r1, 1u << rest[a], 1u << rest[b]) + degree(1u << r0, 1u << r1, 1u << rest[b], 1u << rest[c]);
+      for (int j1 = 0; j1 < 3 && nrest >= 3; ++j1) {
+        const uint32_t c1 = code(rp.rbits[j1]);
+        for (int ca = 0; ca < 4; ++ca)
+          for (int cb = 0; cb < 4; ++cb)
+            for (int cc = 0; cc < 4; ++cc) {
+              int need[4] = {0, 0, 0, 0};
+              ++need[ca];
+              ++need[cb];
+              ++need[cc];
+              if (need[0] > (int)by_cls[0].size() || need[1] > (int)by_cls[1].size() || need[2] > (int)by_cls[2].size() ||
+                  need[3] > (int)by_cls[3].size())
+                continue;
+              const int cost = (1 << (3 - __builtin_popcount(c1 | cls_code[ca] | cls_code[cb]))) +
+                               (1 << (3 - __builtin_popcount(c1 | cls_code[cb] | cls_code[cc])));
               if (cost < best_cost) {
                 best_cost = cost;
-                for (int j = 0; j < 3; ++j) best_r[j] = rp.rbits[pm[j]];
-                best_i[0] = a;
-                best_i[1] = b;
-                best_i[2] = c;
+                best_r1 = j1;
+                best_c[0] = ca;
+                best_c[1] = cb;
+                best_c[2] = cc;
               }
             }
+      }
+      int best_r[3], best_i[3] = {-1, -1, -1};
+      {  // register order: r1 = the chosen bit, r0 / r2 = the other two in their given order
+        int o = 0, others[2];
+        for (int j = 0; j < 3; ++j)
+          if (j != best_r1) others[o++] = rp.rbits[j];
+        best_r[0] = others[0];
+        best_r[1] = rp.rbits[best_r1];
+        best_r[2] = others[1];
+      }
+      if (best_cost < (1 << 30)) {
+        size_t taken[4] = {0, 0, 0, 0};
+        for (int j = 0; j < 3; ++j) {
+          const int lb = by_cls[best_c[j]][taken[best_c[j]]++];
+          for (int i = 0; i < nrest; ++i)
+            if (rest[i] == lb) best_i[j] = i;
+        }
+        round_cost = best_cost;
       }
       for (int j = 0; j < 3; ++j) rp.rbits[j] = best_r[j];
       if (best_i[0] >= 0)
@@ -318,6 +343,7 @@ inline std::vector<RoundPlan> schedule_rounds(const std::vector<Op>& all, const 
     for (int lb : rest)
       if (lb >= 0) order[next_free()] = lb;
     for (int j = 0; j < 9; ++j) rp.item_bit[j] = (j < ni && order[j] >= 0) ? order[j] : 0;
+    return round_cost;
   };
 
   const int n_rounds = (int)rounds.size();
@@ -341,18 +367,28 @@ inline std::vector<RoundPlan> schedule_rounds(const std::vector<Op>& all, const 
         uint32_t W = Nd;
         for (int lb = k - 1; lb >= 0 && __builtin_popcount(W) < 3; --lb)  // high slot bits first: the low ones serve the lanes
           if (((F >> lb) & 1u) && !((W >> lb) & 1u)) W |= 1u << lb;
+        // a chain saves group barriers but pins the warp bits; when that costs bank conflicts (variant qubits on
+        // the low slots leave too few bank-moving bits for the lanes) the rounds run unchained
+        std::vector<RoundPlan> chained(rounds.begin() + i, rounds.begin() + j), apart(rounds.begin() + i, rounds.begin() + j);
+        int cost_chained = 0, cost_apart = 0;
         for (int r = i; r < j; ++r) {
-          assign_items(rounds[r], used_of[r], vtile_of[r], W);
-          rounds[r].chain_next = r + 1 < j;
+          cost_chained += assign_items(chained[r - i], used_of[r], vtile_of[r], W);
+          chained[r - i].chain_next = r + 1 < j;
+          cost_apart += assign_items(apart[r - i], used_of[r], vtile_of[r], 0);
         }
+        const bool keep_chain = always_chain || cost_chained <= cost_apart;
+        const std::vector<RoundPlan>& pick = keep_chain ? chained : apart;
+        for (int r = i; r < j; ++r) rounds[r] = pick[r - i];
+        total_cost += keep_chain ? cost_chained : cost_apart;
       } else {
-        assign_items(rounds[i], used_of[i], vtile_of[i], 0);
+        total_cost += assign_items(rounds[i], used_of[i], vtile_of[i], 0);
       }
       i = j;
     }
   } else {
-    for (int r = 0; r < n_rounds; ++r) assign_items(rounds[r], used_of[r], vtile_of[r], 0);
+    for (int r = 0; r < n_rounds; ++r) total_cost += assign_items(rounds[r], used_of[r], vtile_of[r], 0);
   }
+  if (conflict_cost) *conflict_cost = total_cost;
   return rounds;
 }
 
@@ -436,6 +472,67 @@ inline bool tma_tile_geometry(const std::vector<int>& tile, int n_local, TmaTile
   if (ns != k || g->box_log2 + g->n_enum != k) return false;
   if (g->box_log2 < 6) return false;  // every op must land on a 1024 B boundary (128 B swizzle atom = 8 rows)
   return true;
+}
+
+// The same geometry with tensor dimensions 1.. in another order (every dimension carries its own stride, so any order
+// is a valid tensor map).  order[i] = dimension of `base` that becomes dimension 1 + i, for i < base.n_dims - 1.
+// Only the shared-memory slot order of the boxed qubits changes: the box is laid out dimension by dimension.
+inline TmaTileGeom tma_reorder_dims(const TmaTileGeom& base, const int* order) {
+  TmaTileGeom g = base;
+  int ns = 3;
+  for (int i = 0; i + 1 < base.n_dims; ++i) {
+    const int d = order[i];
+    g.dim_lo[1 + i] = base.dim_lo[d];
+    g.dim_bits[1 + i] = base.dim_bits[d];
+    g.box_bits[1 + i] = base.box_bits[d];
+    for (int b = 0; b < base.box_bits[d]; ++b) g.slot_qubit[ns++] = base.dim_lo[d] + b;
+  }
+  for (int j = 0; j < base.n_enum; ++j) g.slot_qubit[ns++] = base.enum_pos[j];
+  return g;
+}
+
+// Rounds of a pass on the TMA pipeline (swizzle_kind 2) with the dimension order whose slot layout gives the DMMA
+// rounds the fewest shared-memory bank conflicts: slot bits 3..5 are the only ones besides 0..2 that move the bank
+// (tswz), so which boxed qubits land there decides whether a round on high qubits can be conflict-free.
+// plan_sorted.tile is ascending; *plan_slots receives the plan with the tile in the chosen slot order.
+inline std::vector<RoundPlan> schedule_rounds_best_layout(const std::vector<Op>& all, const PassPlan& plan_sorted, const TmaTileGeom& base,
+                                                          int max_variant_bits, TmaTileGeom* chosen, PassPlan* plan_slots, int* cost_out = nullptr,
+                                                          bool always_chain = false, bool search = true) {
+  const int k = base.k, nd = base.n_dims - 1;
+  int boxed[4], n_boxed = 0, plain[4], n_plain = 0;
+  for (int d = 1; d <= nd; ++d) {
+    if (base.box_bits[d] > 0) boxed[n_boxed++] = d;
+    else plain[n_plain++] = d;
+  }
+  std::vector<RoundPlan> best_rounds;
+  int best_cost = 1 << 30;
+  auto consider = [&](const TmaTileGeom& g) {  // true: nothing can beat it
+    PassPlan plan = plan_sorted;
+    for (int j = 0; j < k; ++j) plan.tile[j] = g.slot_qubit[j];
+    int cost = 0;
+    std::vector<RoundPlan> rounds = schedule_rounds(all, plan, max_variant_bits, 2, &cost, always_chain);
+    if (cost < best_cost) {
+      best_cost = cost;
+      best_rounds.swap(rounds);
+      *chosen = g;
+      *plan_slots = plan;
+    }
+    return best_cost <= 2 * (int)best_rounds.size();  // every round conflict-free
+  };
+  bool done = consider(base);  // the ascending order first: it wins ties
+  int perm[4] = {0, 1, 2, 3};
+  while (!done && search) {
+    int order[4];
+    for (int i = 0; i < n_boxed; ++i) order[i] = boxed[perm[i]];
+    for (int i = 0; i < n_plain; ++i) order[n_boxed + i] = plain[i];
+    const TmaTileGeom g = tma_reorder_dims(base, order);
+    bool same = true;
+    for (int j = 0; j < k; ++j) same = same && g.slot_qubit[j] == base.slot_qubit[j];
+    if (!same) done = consider(g);
+    if (!std::next_permutation(perm, perm + n_boxed)) break;
+  }
+  if (cost_out) *cost_out = best_cost;
+  return best_rounds;
 }
 
 // ---- round matrices ---------------------------------------------------------------------------------

@@ -177,12 +177,19 @@ int hl_round_matrices(const qcsim_gate* gates, int count, unsigned long long til
 // ---- TMA-staged pass (planner.h: tma_tile_geometry; fusion.cu: launch_pass_pipe) ------------------
 extern "C" {
 // geometry of a tile set: out = {n_dims, n_enum, box_log2, dim_lo[5], dim_bits[5], box_bits[5], enum_pos[9], slot_qubit[12]}
+static void export_geometry(const TmaTileGeom& g, int* out);
 int hl_tma_geometry(unsigned long long tile_mask, int n_local, int* out) {
   std::vector<int> tile;
   for (int q = 0; q < 64; ++q)
     if ((tile_mask >> q) & 1ULL) tile.push_back(q);
   TmaTileGeom g;
   if (!tma_tile_geometry(tile, n_local, &g)) return 0;
+  export_geometry(g, out);
+  return 1;
+}
+}
+
+static void export_geometry(const TmaTileGeom& g, int* out) {
   int o = 0;
   out[o++] = g.n_dims;
   out[o++] = g.n_enum;
@@ -192,13 +199,16 @@ int hl_tma_geometry(unsigned long long tile_mask, int n_local, int* out) {
   for (int d = 0; d < 5; ++d) out[o++] = g.box_bits[d];
   for (int j = 0; j < 9; ++j) out[o++] = j < g.n_enum ? g.enum_pos[j] : 0;
   for (int j = 0; j < 12; ++j) out[o++] = j < g.k ? g.slot_qubit[j] : 0;
-  return 1;
 }
 
-// Exactly what launch_pass_pipe hands to k_tile_pipe for ONE pass over `tile_mask` (12 qubits): the tile in
+extern "C" {
+
+// Exactly what launch_pass_pipe hands to k_tile_pipe for ONE pass over `tile_mask` (11 qubits): the tensor-map
+// geometry with the dimension order chosen against bank conflicts (geom_out, layout of hl_tma_geometry), the tile in
 // slot order, the rounds scheduled against the TMA swizzle, their descriptors (6 uint32 each: rb, tb[3], var,
 // mat_off) and matrices.  Returns the number of rounds, or -1.
-int hl_pipe_pass(const qcsim_gate* gates, int count, unsigned long long tile_mask, int n_local, unsigned* desc, double* mats, int max_mats) {
+int hl_pipe_pass(const qcsim_gate* gates, int count, unsigned long long tile_mask, int n_local, unsigned* desc, double* mats, int max_mats,
+                 int* geom_out, int layout_search) {
   std::vector<Op> ops;
   PassPlan plan;
   for (int q = 0; q < 64; ++q)
@@ -207,13 +217,14 @@ int hl_pipe_pass(const qcsim_gate* gates, int count, unsigned long long tile_mas
     ops.push_back(classify(gates[i].nq, gates[i].m, gates[i].flags, gates[i].q, gates[i].c1, gates[i].c2));
     if (ops.back().kind != OP_NOP) plan.ops.push_back(i);
   }
-  TmaTileGeom g;
-  if (!tma_tile_geometry(plan.tile, n_local, &g)) return -1;
-  for (int j = 0; j < g.k; ++j) plan.tile[j] = g.slot_qubit[j];
+  TmaTileGeom base, g;
+  if (!tma_tile_geometry(plan.tile, n_local, &base)) return -1;
+  const PassPlan sorted_plan = plan;
+  const std::vector<RoundPlan> rounds = schedule_rounds_best_layout(ops, sorted_plan, base, 3, &g, &plan, nullptr, false, layout_search != 0);
+  export_geometry(g, geom_out);
   int local_of[64];
   for (int q = 0; q < 64; ++q) local_of[q] = -1;
   for (int j = 0; j < g.k; ++j) local_of[plan.tile[j]] = j;
-  const std::vector<RoundPlan> rounds = schedule_rounds(ops, plan, 3, 2);
   int used = 0;
   for (size_t r = 0; r < rounds.size(); ++r) {
     const int nv = (int)rounds[r].vq.size();
@@ -293,8 +304,8 @@ int hl_pipe_conflicts(const qcsim_gate* gates, int count, int n_local, int* hist
     TmaTileGeom g;
     if (!tma_tile_geometry(st.pass.tile, n_local, &g)) continue;
     PassPlan plan = st.pass;
-    for (int j = 0; j < 11; ++j) plan.tile[j] = g.slot_qubit[j];
-    const std::vector<RoundPlan> rplan = schedule_rounds(ops, plan, 3, 2);
+    TmaTileGeom base = g;
+    const std::vector<RoundPlan> rplan = schedule_rounds_best_layout(ops, st.pass, base, 3, &g, &plan);
     for (const RoundPlan& rp : rplan) {
       ++rounds;
       if (rp.chain_next) ++*chained;
@@ -324,8 +335,8 @@ void hl_pipe_round_dump(const qcsim_gate* gates, int count, int n_local) {
     TmaTileGeom g;
     if (!tma_tile_geometry(st.pass.tile, n_local, &g)) continue;
     PassPlan plan = st.pass;
-    for (int j = 0; j < 11; ++j) plan.tile[j] = g.slot_qubit[j];
-    const std::vector<RoundPlan> rplan = schedule_rounds(ops, plan, 3, 2);
+    TmaTileGeom base = g;
+    const std::vector<RoundPlan> rplan = schedule_rounds_best_layout(ops, st.pass, base, 3, &g, &plan);
     printf("pass slots:");
     for (int j = 0; j < 11; ++j) printf(" %d", g.slot_qubit[j]);
     printf("  (boxed 2^%d, enum %d)\n", g.box_log2, g.n_enum);

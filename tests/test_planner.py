@@ -328,7 +328,13 @@ def _geometry(hl, tile_mask, n_local):
     ok = hl.hl_tma_geometry(C.c_ulonglong(tile_mask), n_local, out)
     if not ok:
         return None
-    o = list(out)
+    return _parse_geometry(list(out))
+
+
+_CHAINED = []  # chained rounds seen by each emulated pass (checked after all of them ran)
+
+
+def _parse_geometry(o):
     g = {"n_dims": o[0], "n_enum": o[1], "box_log2": o[2], "dim_lo": o[3:8], "dim_bits": o[8:13], "box_bits": o[13:18],
          "enum_pos": o[18:27][: o[1]], "slot_qubit": o[27:39]}
     return g
@@ -404,9 +410,10 @@ def test_tma_tile_geometry_addresses_every_tile_amplitude_once(hl, n_local, tile
             assert idx == want, (slot, idx, want)
 
 
+@pytest.mark.parametrize("layout_search", [1, 0])
 @pytest.mark.parametrize("seed,n,tile_bits", [(1, 13, range(11)), (2, 14, [0, 1, 2, 3, 6, 7, 8, 9, 10, 12, 13]),
                                               (3, 15, [0, 1, 2, 3, 5, 6, 8, 9, 12, 13, 14]), (4, 16, [0, 1, 2, 8, 9, 10, 11, 12, 13, 14, 15])])
-def test_pipe_kernel_data_path_emulated(hl, seed, n, tile_bits):
+def test_pipe_kernel_data_path_emulated(hl, seed, n, tile_bits, layout_search):
     tile_mask = _mask(tile_bits)
     """k_tile_pipe emulated in numpy from exactly what launch_pass_pipe gives it: TMA ops into swizzled slots, rounds in
     the kernel's MMA mapping (lane (g, t): B fragment = amplitudes t, 4 + t of item g; D fragment = output amplitude g of
@@ -434,15 +441,21 @@ def test_pipe_kernel_data_path_emulated(hl, seed, n, tile_bits):
     arr = pack(circ)
     N = len(circ)
     assert N > 15
-    geom = _geometry(hl, tile_mask, n)
-    assert geom is not None
+    base_geom = _geometry(hl, tile_mask, n)
+    assert base_geom is not None
     R = N + 4
     desc = (C.c_uint * (6 * R))()
     max_mats = 8 * R
     mats = (C.c_double * (128 * max_mats))()
     hl.hl_pipe_pass.restype = C.c_int
-    nr = hl.hl_pipe_pass(arr, N, C.c_ulonglong(tile_mask), n, desc, mats, max_mats)
+    geom_out = (C.c_int * 64)()
+    nr = hl.hl_pipe_pass(arr, N, C.c_ulonglong(tile_mask), n, desc, mats, max_mats, geom_out, layout_search)
     assert 0 < nr < N
+    geom = _parse_geometry(list(geom_out))                                # dimension order chosen against bank conflicts
+    assert sorted(geom["slot_qubit"][:K]) == sorted(base_geom["slot_qubit"][:K]) and geom["slot_qubit"][:3] == [0, 1, 2]
+    assert geom["box_log2"] == base_geom["box_log2"] and geom["enum_pos"] == base_geom["enum_pos"]
+    if not layout_search:
+        assert geom == base_geom
     M = np.frombuffer(mats, dtype=np.complex128).reshape(max_mats, 8, 8)
     psi = random_state(n, 5)
     want = psi.copy()
@@ -534,4 +547,9 @@ def test_pipe_kernel_data_path_emulated(hl, seed, n, tile_bits):
     # bank conflicts of the fragment accesses: the planner picks the register-bit order and item bits 0..2 to dodge them;
     # what remains is forced by register bits that sit above slot bit 5 (the TMA swizzle does not fold those)
     assert max(degrees) <= 2 and np.mean(degrees) < 1.7, (max(degrees), np.mean(degrees))
-    assert n_chained >= 1                                                # some rounds really are chained
+    _CHAINED.append(n_chained)
+
+
+def test_some_emulated_rounds_were_chained():
+    """runs after test_pipe_kernel_data_path_emulated: the chained (warp-local, barrier-free) round hand-over was exercised"""
+    assert _CHAINED and sum(_CHAINED) >= 1, _CHAINED
