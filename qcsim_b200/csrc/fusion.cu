@@ -32,9 +32,11 @@ int env_int(const char* name, int dflt) {
 
 }  // namespace
 
-constexpr size_t kPipeSmemBytes =
-    1024 /* alignment slack */ + (size_t)kPipeStages * kPipeTileBytes + (size_t)kMaxTileMats * kRoundMatAmps * sizeof(amp) +
-    2 * kPipeStages * sizeof(uint64_t) + kMaxTileRounds * sizeof(RoundTable);
+// head (round matrices, mbarriers, round tables, padded to the first 32 KiB boundary of the shared window) + tile ring
+constexpr size_t kPipeHeadUsed = 16 + (size_t)kMaxTileMats * kRoundMatAmps * sizeof(amp) + 2 * kPipeStages * sizeof(uint64_t) +
+                                 kMaxTileRounds * sizeof(RoundTable);
+static_assert(kPipeHeadUsed + 1024 /* the window's reserved first KiB */ <= pipe::kPipeHeadBytes, "head does not fit below the first tile");
+constexpr size_t kPipeSmemBytes = pipe::kPipeHeadBytes + (size_t)kPipeStages * kPipeTileBytes;
 static_assert(kPipeSmemBytes <= 227 * 1024, "shared memory per CTA");
 
 int fusion_init_device_kernels() {  // per device, from engine_create

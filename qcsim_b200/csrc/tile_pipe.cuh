@@ -133,6 +133,14 @@ namespace pipe {
 __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
+// D = A * B + C with D and C in different registers (C stays live)
+__device__ __forceinline__ void dmma884(double (&d)[2], double a, double b, const double (&c)[2]) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%4, %5};" : "=d"(d[0]), "=d"(d[1]) : "d"(a), "d"(b), "d"(c[0]), "d"(c[1]));
+}
+// x with its sign flipped when `flip` is 1 (one integer XOR on the high word)
+__device__ __forceinline__ double flip_sign(double x, uint32_t flip) {
+  return __hiloint2double(__double2hiint(x) ^ (int)(flip << 31), __double2loint(x));
+}
 }  // namespace pipe
 
 namespace pipe {
@@ -162,6 +170,31 @@ __device__ __forceinline__ Smem carve(unsigned char* raw) {
   m.done = m.full + kPipeStages;
   return m;
 }
+// k_tile_pipe's carve: per-pass tables, mbarriers and round tables first, then the tile buffers on a 32 KiB boundary of
+// the shared window -- a tile's base address then has its low 15 bits clear and every fragment address of a round is
+// an XOR of precomputed parts (no adds).  `extra` = bytes needed behind the mbarriers (round tables).
+constexpr uint32_t kPipeHeadBytes = 32768;  // tables + mbarriers + round tables + the pad up to the boundary (the window starts at 1 KiB)
+__device__ __forceinline__ Smem carve_tiles_aligned(unsigned char* raw, uint32_t extra) {
+  Smem m;
+  const uint32_t sa0 = smem_u32(raw);
+  unsigned char* const al = raw + ((16u - (sa0 & 15u)) & 15u);
+  m.tables = reinterpret_cast<amp*>(al);
+  m.full = reinterpret_cast<uint64_t*>(m.tables + (size_t)kMaxTileMats * kRoundMatAmps);
+  m.done = m.full + kPipeStages;
+  const uint32_t head_end = smem_u32(m.done + kPipeStages) + extra;
+  const uint32_t tiles_sa = (head_end + 32767u) & ~32767u;
+  uint32_t dyn;
+  asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
+  if (tiles_sa + kPipeStages * kPipeTileBytes > sa0 + dyn) __trap();  // the launch did not provide the head room
+  m.tiles = reinterpret_cast<amp*>(raw + (tiles_sa - sa0));
+  return m;
+}
+__device__ __forceinline__ double lds_f64(uint32_t sa) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(sa));  // volatile: stays ordered with the barrier / mbarrier asm
+  return v;
+}
+__device__ __forceinline__ void sts_f64(uint32_t sa, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(sa), "d"(v)); }
 __device__ __forceinline__ void init_barriers(const Smem& m) {
   if (threadIdx.x == 0) {
 #pragma unroll
@@ -233,6 +266,7 @@ __device__ __forceinline__ void producer(const PipeGeom& G, const Smem& m) {
 
 // per-round lookup tables of k_tile_pipe (shared memory, filled once per CTA)
 struct RoundTable {
+  // byte offsets inside a tile (swizzled slot * 16), combined by XOR
   uint32_t load_g[8], store_g[8], load_t[4], store_t[4], warp_hi[8], warp_ms[8];
   uint32_t x_hi, x_i0, x_p0, x_p1;
   uint32_t chain_next;  // the next round keeps every warp on its own amplitudes: __syncwarp() instead of the group barrier
@@ -243,7 +277,7 @@ struct RoundTable {
 static __global__ void __launch_bounds__(kPipeThreads, 1) k_tile_pipe(const __grid_constant__ PipePassArgs A) {
   using namespace pipe;
   extern __shared__ __align__(16) unsigned char pipe_smem[];
-  const Smem sm = carve(pipe_smem);
+  const Smem sm = carve_tiles_aligned(pipe_smem, kMaxTileRounds * (uint32_t)sizeof(RoundTable));
   amp* const tiles = sm.tiles;
   amp* const smats = sm.tables;
   uint64_t* const full = sm.full;
@@ -253,7 +287,12 @@ static __global__ void __launch_bounds__(kPipeThreads, 1) k_tile_pipe(const __gr
   init_barriers(sm);
   // round matrices: parameter block -> shared memory once per CTA (a lane reads two entries per round; per-lane
   // addresses would serialise in the constant cache)
-  for (uint32_t i = tid; i < (uint32_t)A.n_mats * kRoundMatAmps; i += kPipeThreads) smats[i] = A.mats[i];
+  // Entry [o][a] of a matrix goes to slot (a >> 2) * 32 + o * 4 + (a & 3): lane (g, t) of a warp reads entries [g][t] and
+  // [g][4 + t], i.e. slots `lane` and 32 + lane -- two conflict-free LDS.128 (row-major slots g * 8 + t were 2-way).
+  for (uint32_t i = tid; i < (uint32_t)A.n_mats * kRoundMatAmps; i += kPipeThreads) {
+    const uint32_t e = i & 63u, o = e >> 3, a = e & 7u;
+    smats[(i & ~63u) + ((a >> 2) << 5) + (o << 2) + (a & 3u)] = A.mats[i];
+  }
   __syncthreads();
 
   if (warp == kPipeConsumerWarps) {
@@ -263,16 +302,16 @@ static __global__ void __launch_bounds__(kPipeThreads, 1) k_tile_pipe(const __gr
 
   // ------------------------------------ consumer warps: the rounds ------------------------------------
   // Round r multiplies every group of 8 amplitudes that differ in the round's 3 register bits by an 8x8 complex
-  // matrix M (one per value of the variant bits).  As a real product: [Re o; Im o] = [Re M, -Im M; Im M, Re M] [Re v; Im v].
-  // MMA mapping (per warp, 4 panels of 8 items): rows = output amplitude o (8) x part (2 M-blocks), columns = items,
-  // contraction = input amplitude a (8) x part = 4 K-blocks: kb = 2 part + (a >> 2), k = a & 3.
-  //   lane (g = lane >> 2, t = lane & 3) holds   A: M[g][t], M[g][4 + t] (16 registers, loaded once per round)
-  //                                              B: amplitudes t and 4 + t of item g of the panel (4 LDS.64)
-  //                                              D: output amplitude g of items 2t and 2t + 1 (4 STS.64)
+  // matrix M (one per value of the variant bits), as THREE real 8x8 products on the FP64 tensor path (the 3-multiplication
+  // form of the complex product; the plain real form [Re M, -Im M; Im M, Re M] needs four).
+  // MMA mapping (per warp, 4 panels of 8 items): rows = output amplitude o, columns = items, contraction = input amplitude
+  // a in 2 K-blocks (a >> 2), k = a & 3:
+  //   lane (g = lane >> 2, t = lane & 3) holds   A: entries [g][t], [g][4 + t] of the three real matrices (from M, once per round)
+  //                                              B: amplitudes t and 4 + t of item g of the panel (4 LDS.64: both halves of each)
+  //                                              D: output amplitude g of items 2t and 2t + 1 (4 STS.64: both halves of each)
   // Fragments move as 64-bit halves: odd k-lanes (t & 1) fetch the imaginary half first, odd rows (g & 1) store it
-  // first, and the K-blocks / row blocks are permuted to match (a_first / a_second below).  A half-warp then covers
-  // 16 distinct 8-byte columns of a 128 B row even when register bit 0 sits where the TMA swizzle does not fold
-  // (planner.h, swizzle_kind 2).
+  // first.  A half-warp then covers 16 distinct 8-byte columns of a 128 B row even when register bit 0 sits where the
+  // TMA swizzle does not fold (planner.h, swizzle_kind 2); the parity is absorbed by the operands (see the round body).
   // Item index (8 bits): bits 0..2 = column in the panel, bits 3..4 = panel, bits 5..7 = warp of the group.
   // Two consumer groups take alternate tiles, each with its own named barrier: while one group waits for its
   // fragment loads or its round barrier, the other keeps the fp64 pipe busy.
@@ -292,16 +331,16 @@ static __global__ void __launch_bounds__(kPipeThreads, 1) k_tile_pipe(const __gr
     const uint32_t rb0 = 1u << (rd.rb & 31u), rb1 = 1u << ((rd.rb >> 8) & 31u), rb2 = 1u << ((rd.rb >> 16) & 31u);
     auto ib = [&](int q) { return 1u << ((rd.tb[q >> 2] >> (8 * (q & 3))) & 31u); };  // slot bit walked by item bit q
     if (j < 8) {  // loads: item g of the panel
-      rt[r].load_g[j] = tswz(((j & 1u) ? ib(0) : 0u) | ((j & 2u) ? ib(1) : 0u) | ((j & 4u) ? ib(2) : 0u));
+      rt[r].load_g[j] = tswz(((j & 1u) ? ib(0) : 0u) | ((j & 2u) ? ib(1) : 0u) | ((j & 4u) ? ib(2) : 0u)) << 4;
     } else if (j < 16) {  // stores: amplitude g
       const uint32_t x = j - 8;
-      rt[r].store_g[x] = tswz(((x & 1u) ? rb0 : 0u) | ((x & 2u) ? rb1 : 0u) | ((x & 4u) ? rb2 : 0u));
+      rt[r].store_g[x] = tswz(((x & 1u) ? rb0 : 0u) | ((x & 2u) ? rb1 : 0u) | ((x & 4u) ? rb2 : 0u)) << 4;
     } else if (j < 20) {  // loads: amplitudes tq (+4)
       const uint32_t x = j - 16;
-      rt[r].load_t[x] = tswz(((x & 1u) ? rb0 : 0u) | ((x & 2u) ? rb1 : 0u));
+      rt[r].load_t[x] = (tswz(((x & 1u) ? rb0 : 0u) | ((x & 2u) ? rb1 : 0u)) << 4) | ((x & 1u) << 3);  // + the half fetched first
     } else if (j < 24) {  // stores: items 2 tq (+1)
       const uint32_t x = j - 20;
-      rt[r].store_t[x] = tswz(((x & 1u) ? ib(1) : 0u) | ((x & 2u) ? ib(2) : 0u));
+      rt[r].store_t[x] = tswz(((x & 1u) ? ib(1) : 0u) | ((x & 2u) ? ib(2) : 0u)) << 4;
     } else if (j < 32) {  // warp part of the item index, and the matrix the warp uses
       const uint32_t w = j - 24;
       uint32_t hi = 0;
@@ -315,13 +354,13 @@ static __global__ void __launch_bounds__(kPipeThreads, 1) k_tile_pipe(const __gr
           else vidx |= ((hi >> (en >> 1)) & 1u) << q;
         }
       }
-      rt[r].warp_hi[w] = tswz(hi);
+      rt[r].warp_hi[w] = tswz(hi) << 4;
       rt[r].warp_ms[w] = gs | ((rd.mat_off + vidx) << 24);
     } else if (j == 32) {
-      rt[r].x_hi = tswz(rb2);
-      rt[r].x_i0 = tswz(ib(0));
-      rt[r].x_p0 = tswz(ib(3));
-      rt[r].x_p1 = tswz(ib(4));
+      rt[r].x_hi = tswz(rb2) << 4;
+      rt[r].x_i0 = tswz(ib(0)) << 4;
+      rt[r].x_p0 = tswz(ib(3)) << 4;
+      rt[r].x_p1 = tswz(ib(4)) << 4;
       rt[r].chain_next = (rd.var >> 7) & 1u;
     }
   }
@@ -329,7 +368,7 @@ static __global__ void __launch_bounds__(kPipeThreads, 1) k_tile_pipe(const __gr
 
   for (uint64_t t = blockIdx.x + (uint64_t)group * gridDim.x, i = group; t < A.geom.n_tiles; t += (uint64_t)kPipeGroups * gridDim.x, i += kPipeGroups) {
     const int s = (int)(i % kPipeStages);
-    amp* const tile = tiles + (size_t)s * (1u << kPipeTileBits);
+    const uint32_t tile_sa = smem_u32(tiles) + (uint32_t)s * kPipeTileBytes;  // low 15 bits clear
     const uint64_t gbase = gbase_of(A.geom, t);
     mbar_wait(&full[s], (uint32_t)(i / kPipeStages) & 1u);
 
@@ -338,7 +377,10 @@ static __global__ void __launch_bounds__(kPipeThreads, 1) k_tile_pipe(const __gr
       {
         const RoundTable& T = rt[r];
         const uint32_t wh = T.warp_hi[gwarp], wm = T.warp_ms[gwarp];
-        const uint32_t ld0 = wh ^ T.load_g[g] ^ T.load_t[tq], st0 = wh ^ T.store_g[g] ^ T.store_t[tq];
+        const uint32_t lq = tq & 1u, sq = g & 1u;  // half taken first by this lane's loads / stores (0 = real)
+        // shared-window byte addresses of this lane's fragment halves: tile base ^ warp part ^ lane parts (^ panel part)
+        const uint32_t ld0 = tile_sa ^ wh ^ T.load_g[g] ^ T.load_t[tq];                     // first half of amplitude tq, panel 0
+        const uint32_t st0 = tile_sa ^ wh ^ T.store_g[g] ^ T.store_t[tq] ^ (sq << 3);       // first half of output g, item 2 tq, panel 0
         uint32_t midx = wm >> 24;
 #pragma unroll
         for (int j = 0; j < kMaxVariantBits; ++j) {
@@ -347,51 +389,69 @@ static __global__ void __launch_bounds__(kPipeThreads, 1) k_tile_pipe(const __gr
         }
         // A fragments of this warp's matrix
         const amp* __restrict__ M = smats + (size_t)midx * kRoundMatAmps;
-        const double2 m_lo = M[g * 8 + tq], m_hi = M[g * 8 + 4 + tq];
+        const double2 m_lo = M[lane], m_hi = M[32 + lane];
         const uint32_t x_hi = T.x_hi, x_i0 = T.x_i0, x_p0 = T.x_p0, x_p1 = T.x_p1;
-        const double* const td = reinterpret_cast<const double*>(tile);
-        double* const tdw = reinterpret_cast<double*>(tile);
-        const uint32_t lq = tq & 1u, sq = g & 1u;  // half taken first by this lane's loads / stores (0 = real)
-        double b[4][4];                            // [panel][K-block]
+        double b[4][4];                            // [panel]: first half of amplitudes tq, 4 + tq, then their second halves
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
           const uint32_t a0 = ld0 ^ ((p & 1) ? x_p0 : 0u) ^ ((p & 2) ? x_p1 : 0u);
-          b[p][0] = td[2 * a0 + lq];
-          b[p][1] = td[2 * (a0 ^ x_hi) + lq];
-          b[p][2] = td[2 * a0 + (lq ^ 1u)];
-          b[p][3] = td[2 * (a0 ^ x_hi) + (lq ^ 1u)];
+          b[p][0] = lds_f64(a0);
+          b[p][1] = lds_f64(a0 ^ x_hi);
+          b[p][2] = lds_f64(a0 ^ 8u);
+          b[p][3] = lds_f64(a0 ^ x_hi ^ 8u);
         }
-        // contraction element of (K-block j, this lane): part = lq for j < 2, 1 - lq for j >= 2; amplitude tq + 4 (j & 1).
-        // Row blocks: the first accumulator holds the half this lane stores first (Re rows for even g, Im rows for odd g).
-        // Re row of o: [Re M | -Im M] over (Re v | Im v); Im row: [Im M | Re M].
-        const double re_row[4] = {lq ? -m_lo.y : m_lo.x, lq ? -m_hi.y : m_hi.x, lq ? m_lo.x : -m_lo.y, lq ? m_hi.x : -m_hi.y};
-        const double im_row[4] = {lq ? m_lo.x : m_lo.y, lq ? m_hi.x : m_hi.y, lq ? m_lo.y : m_lo.x, lq ? m_hi.y : m_hi.x};
-        double a_first[4], a_second[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          a_first[j] = sq ? im_row[j] : re_row[j];
-          a_second[j] = sq ? re_row[j] : im_row[j];
+        // The parity of the halves is folded into the operands instead of being undone with selects: with
+        // v'_a = (-i)^(a & 1) v_a and o'_o = (-i)^(o & 1) o_o the product is o' = M' v', M'[o][a] = (-i)^(o & 1) i^(a & 1) M[o][a], and
+        //   Re v'_a = the half this lane fetched first,  Im v'_a = +-(the half fetched second)   (- for odd a, i.e. lq),
+        //   Re o'_o = the half this lane stores first,   Im o'_o = +-(the half stored second)    (- for odd o, i.e. sq).
+        // Three real 8x8 products instead of four (M' = P + iQ, v' = x + iy):
+        //   S = P (x + y),   Re o' = S - (P + Q) y,   Im o' = S + (Q - P) x
+        // = 6 DMMA per panel of 8 items: 2 for S, then 2 + 2 that start from S.
+        double2 ml = m_lo, mh = m_hi;
+        if (lq != sq) {  // times i (lq = 1, sq = 0) or -i (lq = 0, sq = 1)
+          ml = lq ? make_double2(-m_lo.y, m_lo.x) : make_double2(m_lo.y, -m_lo.x);
+          mh = lq ? make_double2(-m_hi.y, m_hi.x) : make_double2(m_hi.y, -m_hi.x);
         }
-        double c_first[4][2], c_second[4][2];
+        const double n1[2] = {ml.x, mh.x};
+        const double n2[2] = {-(ml.x + ml.y), -(mh.x + mh.y)};
+        const double n3[2] = {ml.y - ml.x, mh.y - mh.x};
+        double xs[4][2], S[4][2], c_first[4][2], c_second[4][2];
 #pragma unroll
-        for (int p = 0; p < 4; ++p) c_first[p][0] = c_first[p][1] = c_second[p][0] = c_second[p][1] = 0.0;
-        // 8 independent accumulator chains (4 panels x 2 row blocks), 4 K-blocks deep
+        for (int p = 0; p < 4; ++p) {
+          b[p][2] = flip_sign(b[p][2], lq);
+          b[p][3] = flip_sign(b[p][3], lq);
+          xs[p][0] = b[p][0] + b[p][2];
+          xs[p][1] = b[p][1] + b[p][3];
+          S[p][0] = S[p][1] = 0.0;
+        }
 #pragma unroll
-        for (int kb = 0; kb < 4; ++kb) {
+        for (int kb = 0; kb < 2; ++kb) {
 #pragma unroll
-          for (int p = 0; p < 4; ++p) {
-            dmma884(c_first[p], a_first[kb], b[p][kb]);
-            dmma884(c_second[p], a_second[kb], b[p][kb]);
-          }
+          for (int p = 0; p < 4; ++p) dmma884(S[p], n1[kb], xs[p][kb]);
+        }
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          dmma884(c_first[p], n2[0], b[p][2], S[p]);
+          dmma884(c_second[p], n3[0], b[p][0], S[p]);
+        }
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          dmma884(c_first[p], n2[1], b[p][3]);
+          dmma884(c_second[p], n3[1], b[p][1]);
+        }
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          c_second[p][0] = flip_sign(c_second[p][0], sq);
+          c_second[p][1] = flip_sign(c_second[p][1], sq);
         }
         // mma.sync is warp-synchronous: every lane's loads of a panel are complete before any lane stores into it
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
           const uint32_t a0 = st0 ^ ((p & 1) ? x_p0 : 0u) ^ ((p & 2) ? x_p1 : 0u);
-          tdw[2 * a0 + sq] = c_first[p][0];
-          tdw[2 * (a0 ^ x_i0) + sq] = c_first[p][1];
-          tdw[2 * a0 + (sq ^ 1u)] = c_second[p][0];
-          tdw[2 * (a0 ^ x_i0) + (sq ^ 1u)] = c_second[p][1];
+          sts_f64(a0, c_first[p][0]);
+          sts_f64(a0 ^ x_i0, c_first[p][1]);
+          sts_f64(a0 ^ 8u, c_second[p][0]);
+          sts_f64(a0 ^ x_i0 ^ 8u, c_second[p][1]);
         }
         if (r + 1 == A.n_rounds) fence_proxy_async();
         if (T.chain_next && r + 1 < A.n_rounds) __syncwarp();

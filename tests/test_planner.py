@@ -509,16 +509,25 @@ def test_pipe_kernel_data_path_emulated(hl, seed, n, tile_bits, layout_search):
                     for addr in loads:
                         touched_d[addr] += 1
                     bfr = [td[addr] for addr in loads]
-                    # real 16 x 16 product through the fragments: contraction element of (K-block j, lane) is
-                    # (part = lq for j < 2 else 1 - lq, amplitude tq + 4 (j & 1)) of item g
-                    vre = np.zeros((8, 8))
-                    vim = np.zeros((8, 8))
-                    for j in range(4):
-                        part = np.where(j < 2, lq, lq ^ 1)
-                        amp_i = tq4 + 4 * (j & 1)
-                        vre[g[part == 0], amp_i[part == 0]] = bfr[j][part == 0]
-                        vim[g[part == 1], amp_i[part == 1]] = bfr[j][part == 1]
-                    out = (vre + 1j * vim) @ Mv.T                        # out[n][o] = sum_a M[o][a] v[n][a]
+                    # what the lanes hold: first / second fetched half of amplitudes tq and 4 + tq of item g.  With
+                    # v'_a = (-i)^(a & 1) v_a:  Re v' = first half,  Im v' = second half, negated on odd k-lanes
+                    x = np.zeros((8, 8))                                 # [item][amplitude]
+                    y = np.zeros((8, 8))
+                    for j in range(2):
+                        amp_i = tq4 + 4 * j
+                        x[g, amp_i] = bfr[j]
+                        y[g, amp_i] = np.where(lq == 1, -bfr[2 + j], bfr[2 + j])
+                    # M'[o][a] = (-i)^(o & 1) i^(a & 1) M[o][a] = P + iQ;  three real products (6 DMMA per panel):
+                    # S = P (x + y),  Re o' = S - (P + Q) y,  Im o' = S + (Q - P) x
+                    oo, aa = np.meshgrid(np.arange(8), np.arange(8), indexing="ij")
+                    Mp = Mv * ((-1j) ** (oo & 1)) * (1j ** (aa & 1))
+                    P, Q = Mp.real, Mp.imag
+                    S = (x + y) @ P.T
+                    re_o = S + y @ (-(P + Q)).T                          # [item][o]
+                    im_o = S + x @ (Q - P).T
+                    # o'_o = (-i)^(o & 1) o_o: the first stored half is Re o', the second is Im o', negated on odd rows
+                    odd = (np.arange(8) & 1)[None, :]
+                    out = np.where(odd == 1, -im_o + 1j * re_o, re_o + 1j * im_o)   # back to o (checked against the kernel's stores below)
                     s0 = st0 ^ (x_p0 if p & 1 else 0) ^ (x_p1 if p & 2 else 0)
                     o0, o1 = out[2 * tq4, g], out[2 * tq4 + 1, g]        # D fragments: row o = g, columns 2 tq, 2 tq + 1
                     first0 = np.where(sq == 1, o0.imag, o0.real)
