@@ -35,14 +35,21 @@ def needs_build() -> bool:
     return not os.path.exists(LIB) or os.path.getmtime(LIB) < _newest_source_mtime()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile the CUDA extension if it is missing or stale; returns the library path."""
+def build(force: bool = False, verbose: bool = False, out: str | None = None, extra_flags: list[str] | None = None) -> str:
+    """Compile the CUDA extension if it is missing or stale; returns the library path.
+    `out` / `extra_flags` build an experimental variant (e.g. -DQCSIM_PIPE_GROUPS=3) next to the shipped library."""
+    if out is not None:
+        return _compile(out, verbose, extra_flags or [])
     if not force and not needs_build():
         return LIB
+    return _compile(LIB, verbose, [])
+
+
+def _compile(LIB: str, verbose: bool, extra_flags: list[str]) -> str:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libqcsim_b200.so (there is no CPU fallback)")
-    cmd = [nvcc, *NVCC_FLAGS]
+    cmd = [nvcc, *NVCC_FLAGS, *extra_flags]
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += [os.path.join(CSRC, s) for s in SOURCES]

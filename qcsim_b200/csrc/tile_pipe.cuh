@@ -40,13 +40,19 @@ namespace qcsim {
 
 constexpr int kPipeTileBits = 11;                        // 2^11 amplitudes = 32 KiB per tile
 constexpr int kPipeStages = 6;                           // tile buffers in the ring (192 KiB)
-constexpr int kPipeGroups = 2;                           // consumer groups; each works on its own tile
+#ifndef QCSIM_PIPE_GROUPS
+#define QCSIM_PIPE_GROUPS 2
+#endif
+#ifndef QCSIM_PIPE_LOOKAHEAD
+#define QCSIM_PIPE_LOOKAHEAD 4
+#endif
+constexpr int kPipeGroups = QCSIM_PIPE_GROUPS;           // consumer groups; each works on its own tile
 constexpr int kPipeGroupWarps = 8;                       // a warp owns 32 round items = 4 MMA panels of 8 items
 constexpr int kPipeGroupThreads = kPipeGroupWarps * 32;
 constexpr int kPipeConsumerWarps = kPipeGroups * kPipeGroupWarps;
 constexpr int kPipeConsumers = kPipeConsumerWarps * 32;
 constexpr int kPipeThreads = kPipeConsumers + 32;        // + producer warp
-constexpr int kPipeLookahead = 4;                        // tiles requested ahead of the one being drained
+constexpr int kPipeLookahead = QCSIM_PIPE_LOOKAHEAD;     // tiles requested ahead of the one being drained
 constexpr uint32_t kPipeTileBytes = (uint32_t)sizeof(amp) << kPipeTileBits;
 
 // what the producer warp needs: the tensor map and how tile numbers / TMA ops turn into coordinates
@@ -364,7 +370,7 @@ static __global__ void __launch_bounds__(kPipeThreads, 1) k_tile_pipe(const __gr
       rt[r].chain_next = (rd.var >> 7) & 1u;
     }
   }
-  asm volatile("bar.sync 3, %0;" ::"n"(kPipeConsumers) : "memory");  // all consumers (the producer is already moving tiles)
+  asm volatile("bar.sync 8, %0;" ::"n"(kPipeConsumers) : "memory");  // all consumers (the producer is already moving tiles)
 
   for (uint64_t t = blockIdx.x + (uint64_t)group * gridDim.x, i = group; t < A.geom.n_tiles; t += (uint64_t)kPipeGroups * gridDim.x, i += kPipeGroups) {
     const int s = (int)(i % kPipeStages);
@@ -391,6 +397,8 @@ static __global__ void __launch_bounds__(kPipeThreads, 1) k_tile_pipe(const __gr
         const amp* __restrict__ M = smats + (size_t)midx * kRoundMatAmps;
         const double2 m_lo = M[lane], m_hi = M[32 + lane];
         const uint32_t x_hi = T.x_hi, x_i0 = T.x_i0, x_p0 = T.x_p0, x_p1 = T.x_p1;
+        uint32_t chain_next;  // read here, with the other table entries: at the end of the round its latency sat in front of the barrier
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(chain_next) : "r"(smem_u32(&T.chain_next)));
         double b[4][4];                            // [panel]: first half of amplitudes tq, 4 + tq, then their second halves
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
@@ -407,11 +415,11 @@ static __global__ void __launch_bounds__(kPipeThreads, 1) k_tile_pipe(const __gr
         // Three real 8x8 products instead of four (M' = P + iQ, v' = x + iy):
         //   S = P (x + y),   Re o' = S - (P + Q) y,   Im o' = S + (Q - P) x
         // = 6 DMMA per panel of 8 items: 2 for S, then 2 + 2 that start from S.
-        double2 ml = m_lo, mh = m_hi;
-        if (lq != sq) {  // times i (lq = 1, sq = 0) or -i (lq = 0, sq = 1)
-          ml = lq ? make_double2(-m_lo.y, m_lo.x) : make_double2(m_lo.y, -m_lo.x);
-          mh = lq ? make_double2(-m_hi.y, m_hi.x) : make_double2(m_hi.y, -m_hi.x);
-        }
+        // M' = (-i)^sq i^lq M: unchanged when lq == sq, times i (lq = 1) or -i (lq = 0) otherwise; signs by integer XOR (a DADD
+        // negation would queue behind the other warps' DMMA in the FP64 pipe)
+        const bool turn = lq != sq;
+        const double2 ml = turn ? make_double2(flip_sign(m_lo.y, lq), flip_sign(m_lo.x, lq ^ 1u)) : m_lo;
+        const double2 mh = turn ? make_double2(flip_sign(m_hi.y, lq), flip_sign(m_hi.x, lq ^ 1u)) : m_hi;
         const double n1[2] = {ml.x, mh.x};
         const double n2[2] = {-(ml.x + ml.y), -(mh.x + mh.y)};
         const double n3[2] = {ml.y - ml.x, mh.y - mh.x};
@@ -454,7 +462,7 @@ static __global__ void __launch_bounds__(kPipeThreads, 1) k_tile_pipe(const __gr
           sts_f64(a0 ^ x_i0 ^ 8u, c_second[p][1]);
         }
         if (r + 1 == A.n_rounds) fence_proxy_async();
-        if (T.chain_next && r + 1 < A.n_rounds) __syncwarp();
+        if (chain_next && r + 1 < A.n_rounds) __syncwarp();
         else group_bar(group);
       }
     }
