@@ -478,7 +478,7 @@ int qcsim_sv_qubit_probability(qcsim_sv* h, uint64_t q, double* p) {
     double scratch[kMaxWorld];
     return multi_forward(h, [&](qcsim_sv* s, int r) { return qcsim_sv_qubit_probability(s, q, r == 0 ? p : &scratch[r]); });
   }
-  QCSIM_TRY(engine_flush(h));
+  QCSIM_TRY(engine_flush_for_diagonal_observable(h, 1ULL << q));  // gates that cannot change P(q) stay queued
   return engine_masked_norm2(h, 1ULL << q, 1ULL << q, p);
 }
 

@@ -11,6 +11,7 @@
 #include "reduce_kernels.cuh"
 #include "dist.h"
 #include "fusion.h"
+#include "planner.h"
 #include "qft_kernels.cuh"
 
 namespace qcsim {
@@ -482,6 +483,23 @@ int engine_flush(qcsim_sv* h) {
   std::vector<Op> q;
   q.swap(h->queue);
   return fusion_execute(h, q);
+}
+
+// Flush for an observable that is diagonal and acts on the qubits of `qmask` only (planner.h): gates it cannot see
+// stay queued, so a caller that reads one probability per layer still gets whole-circuit fusion.
+int engine_flush_for_diagonal_observable(qcsim_sv* h, uint64_t qmask) {
+  static const int lazy = [] {
+    const char* e = std::getenv("QCSIM_LAZY_OBSERVABLES");
+    return e ? std::atoi(e) : 1;
+  }();
+  if (h->queue.empty()) return QCSIM_OK;
+  if (!lazy) return engine_flush(h);
+  std::vector<Op> needed, rest;
+  split_queue_for_diagonal_observable(h->queue, qmask, &needed, &rest);
+  if (rest.size() < 4) return engine_flush(h);  // nothing worth keeping
+  h->queue.swap(rest);
+  if (needed.empty()) return QCSIM_OK;
+  return fusion_execute(h, needed);
 }
 
 int engine_canonicalize(qcsim_sv* h) {

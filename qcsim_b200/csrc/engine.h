@@ -126,6 +126,7 @@ int engine_apply_operator(qcsim_sv* h, const double* m_row_major);
 int engine_apply_now(qcsim_sv* h, const Op& op);
 int engine_enqueue(qcsim_sv* h, const Op& op);
 int engine_flush(qcsim_sv* h);
+int engine_flush_for_diagonal_observable(qcsim_sv* h, uint64_t qmask);  // gates the observable cannot see stay queued
 void engine_drop_queue(qcsim_sv* h);
 int engine_canonicalize(qcsim_sv* h);
 int engine_qft(qcsim_sv* h, uint64_t sq, uint64_t eq, bool do_swap, bool inverse);

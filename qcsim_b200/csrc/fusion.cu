@@ -148,8 +148,35 @@ static int launch_pass_pipe(qcsim_sv* h, const std::vector<Op>& all, const PassP
     }
     A.n_rounds = n_rounds;
     A.n_mats = (int)mat_index;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (debug > 2) {  // QCSIM_DEBUG_PLAN=3: time every launch (serialises the stream; diagnostics only)
+      CUDA_TRY(cudaEventCreate(&ev0));
+      CUDA_TRY(cudaEventCreate(&ev1));
+      CUDA_TRY(cudaEventRecord(ev0, h->stream));
+    }
     k_tile_pipe<<<(unsigned)grid, kPipeThreads, kPipeSmemBytes, h->stream>>>(A);
     CUDA_TRY(cudaGetLastError());
+    if (debug > 2) {
+      CUDA_TRY(cudaEventRecord(ev1, h->stream));
+      CUDA_TRY(cudaEventSynchronize(ev1));
+      float ms = 0;
+      CUDA_TRY(cudaEventElapsedTime(&ms, ev0, ev1));
+      int chained = 0;
+      for (int q = 0; q < n_rounds; ++q) chained += (A.rounds[q].var >> 7) & 1;
+      std::fprintf(stderr, "[qcsim pipe launch] rounds=%d chained=%d matrices=%zu enum=%d ms=%.3f\n", n_rounds, chained, mat_index, g.n_enum, ms);
+#ifdef QCSIM_PIPE_PROFILE
+      unsigned long long pr[16], zero[16] = {0};
+      CUDA_TRY(cudaMemcpyFromSymbol(pr, g_pipe_prof, sizeof(pr)));
+      CUDA_TRY(cudaMemcpyToSymbol(g_pipe_prof, zero, sizeof(zero)));
+      const double w = (double)pr[7], cta = w / kPipeConsumerWarps;
+      if (w > 0)
+        std::fprintf(stderr, "[qcsim pipe profile] rounds=%d per consumer warp: total %.0f kcyc, wait tile %.1f%%, rounds %.1f%% (barriers %.1f%%), other %.1f%% | producer: total %.0f kcyc, wait done %.1f%%, wait store reads %.1f%%\n",
+                     n_rounds, pr[0] / w / 1e3, 100.0 * pr[1] / pr[0], 100.0 * pr[2] / pr[0], 100.0 * pr[3] / pr[0], 100.0 * (pr[0] - pr[1] - pr[2]) / (double)pr[0],
+                     pr[4] / cta / 1e3, 100.0 * pr[5] / pr[4], 100.0 * pr[6] / pr[4]);
+#endif
+      cudaEventDestroy(ev0);
+      cudaEventDestroy(ev1);
+    }
     h->stats.kernel_launches += 1;
     h->stats.state_passes += 1;
     h->stats.bytes_moved += 32ULL * h->dim_local;

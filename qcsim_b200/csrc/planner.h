@@ -56,6 +56,30 @@ struct PassPlan {
   std::vector<int> ops;   // indices into the op list, program order
 };
 
+// ---- what a diagonal observable needs from the queue --------------------------------------------
+// GetQubitProbability(q) (QubitRegister.h:211-225) is the expectation of a projector that is diagonal in the computational
+// basis and acts on qubit q only.  A queued gate changes it only if it acts NON-diagonally on q, or has to run before
+// such a gate (it does not commute with it).  Everything else commutes past the needed gates and past the projector:
+// it can stay queued and fuse with the gates that arrive later.  Two gates commute here iff they share qubits only
+// diagonally (controls / diagonal selectors) -- the rule plan_passes uses to reorder.
+// needed / rest keep program order; running `needed` and leaving `rest` queued is the same circuit.
+inline void split_queue_for_diagonal_observable(const std::vector<Op>& queue, uint64_t qmask, std::vector<Op>* needed, std::vector<Op>* rest) {
+  const size_t n = queue.size();
+  std::vector<char> take(n, 0);
+  uint64_t s_nd = 0, s_dg = qmask;  // the needed set so far (scanning backwards), seeded with the observable
+  for (size_t i = n; i-- > 0;) {
+    const OpMasks m = masks_of(queue[i]);
+    if (((m.nd | m.dg) & s_nd) != 0 || (m.nd & s_dg) != 0) {
+      take[i] = 1;
+      s_nd |= m.nd;
+      s_dg |= m.dg;
+    }
+  }
+  needed->clear();
+  rest->clear();
+  for (size_t i = 0; i < n; ++i) (take[i] ? needed : rest)->push_back(queue[i]);
+}
+
 struct PlanStep {
   bool fused;
   PassPlan pass;  // !fused: pass.ops holds the single op index

@@ -149,6 +149,18 @@ __device__ __forceinline__ double flip_sign(double x, uint32_t flip) {
 }
 }  // namespace pipe
 
+#ifdef QCSIM_PIPE_PROFILE
+// diagnostics build only: cycles per phase, summed over warps (lane 0), read back by launch_pass_pipe
+// [0] consumer total  [1] wait for the tile  [2] rounds incl. barriers  [3] barriers  [4] producer total  [5] producer wait done
+// [6] producer wait for store reads  [7] consumer warps counted  [8] first-round loads issued -> round end (round 0 only)
+__device__ unsigned long long g_pipe_prof[16];
+#define PROF_T() clock64()
+#define PROF_ADD(i, v) do { if ((threadIdx.x & 31u) == 0) atomicAdd(&g_pipe_prof[i], (unsigned long long)(v)); } while (0)
+#else
+#define PROF_T() 0LL
+#define PROF_ADD(i, v) do { } while (0)
+#endif
+
 namespace pipe {
 
 // scatter the tile number into the non-tile index bits
@@ -252,19 +264,28 @@ __device__ __forceinline__ void producer(const PipeGeom& G, const Smem& m) {
   for (int j = 0; j < kPipeLookahead; ++j)
     if (blockIdx.x + j * step < G.n_tiles) issue_load(blockIdx.x + j * step, j);
   uint32_t i = 0;
+  const long long p_t0 = PROF_T();
+  long long p_done = 0, p_read = 0;
   for (uint64_t t = blockIdx.x; t < G.n_tiles; t += step, ++i) {
     const int s = (int)(i % kPipeStages);
+    const long long q0 = PROF_T();
     mbar_wait(&m.done[s], (i / kPipeStages) & 1u);  // rounds of tile i finished, fenced for the async proxy
+    p_done += PROF_T() - q0;
     issue_store(t, s);
     const uint64_t t2 = t + kPipeLookahead * step;
     if (t2 < G.n_tiles) {
       // the buffer of tile i + lookahead is the one tile i + lookahead - stages drained from: wait until that
       // drain has been read out of shared memory (all but the most recent stages - lookahead groups)
+      const long long q1 = PROF_T();
       bulk_wait_read<kPipeStages - kPipeLookahead>();
       __syncwarp();
+      p_read += PROF_T() - q1;
       issue_load(t2, (int)((i + kPipeLookahead) % kPipeStages));
     }
   }
+  PROF_ADD(4, PROF_T() - p_t0);
+  PROF_ADD(5, p_done);
+  PROF_ADD(6, p_read);
   bulk_wait<0>();  // all stores complete before the CTA exits
 }
 
@@ -372,11 +393,16 @@ static __global__ void __launch_bounds__(kPipeThreads, 1) k_tile_pipe(const __gr
   }
   asm volatile("bar.sync 8, %0;" ::"n"(kPipeConsumers) : "memory");  // all consumers (the producer is already moving tiles)
 
+  const long long c_t0 = PROF_T();
+  long long c_full = 0, c_rounds = 0, c_bar = 0;
   for (uint64_t t = blockIdx.x + (uint64_t)group * gridDim.x, i = group; t < A.geom.n_tiles; t += (uint64_t)kPipeGroups * gridDim.x, i += kPipeGroups) {
     const int s = (int)(i % kPipeStages);
     const uint32_t tile_sa = smem_u32(tiles) + (uint32_t)s * kPipeTileBytes;  // low 15 bits clear
     const uint64_t gbase = gbase_of(A.geom, t);
+    const long long w0 = PROF_T();
     mbar_wait(&full[s], (uint32_t)(i / kPipeStages) & 1u);
+    const long long w1 = PROF_T();
+    c_full += w1 - w0;
 
 #pragma unroll 1
     for (int r = 0; r < A.n_rounds; ++r) {
@@ -424,54 +450,66 @@ static __global__ void __launch_bounds__(kPipeThreads, 1) k_tile_pipe(const __gr
         const double n2[2] = {-(ml.x + ml.y), -(mh.x + mh.y)};
         const double n3[2] = {ml.y - ml.x, mh.y - mh.x};
         double xs[4][2], S[4][2], c_first[4][2], c_second[4][2];
+#ifndef QCSIM_PIPE_HALF_ROUNDS
+#define QCSIM_PIPE_HALF_ROUNDS 0
+#endif
+        // QCSIM_PIPE_HALF_ROUNDS: the panels go through DMMA and out to shared memory two at a time, so that the first
+        // half's stores run under the second half's DMMA (experiment switch; 0 = all four panels at once)
+        constexpr int kPanelsAtOnce = QCSIM_PIPE_HALF_ROUNDS ? 2 : 4;
 #pragma unroll
-        for (int p = 0; p < 4; ++p) {
-          b[p][2] = flip_sign(b[p][2], lq);
-          b[p][3] = flip_sign(b[p][3], lq);
-          xs[p][0] = b[p][0] + b[p][2];
-          xs[p][1] = b[p][1] + b[p][3];
-          S[p][0] = S[p][1] = 0.0;
-        }
+        for (int p0 = 0; p0 < 4; p0 += kPanelsAtOnce) {
 #pragma unroll
-        for (int kb = 0; kb < 2; ++kb) {
+          for (int p = p0; p < p0 + kPanelsAtOnce; ++p) {
+            b[p][2] = flip_sign(b[p][2], lq);
+            b[p][3] = flip_sign(b[p][3], lq);
+            xs[p][0] = b[p][0] + b[p][2];
+            xs[p][1] = b[p][1] + b[p][3];
+            S[p][0] = S[p][1] = 0.0;
+          }
 #pragma unroll
-          for (int p = 0; p < 4; ++p) dmma884(S[p], n1[kb], xs[p][kb]);
-        }
+          for (int kb = 0; kb < 2; ++kb) {
 #pragma unroll
-        for (int p = 0; p < 4; ++p) {
-          dmma884(c_first[p], n2[0], b[p][2], S[p]);
-          dmma884(c_second[p], n3[0], b[p][0], S[p]);
-        }
+            for (int p = p0; p < p0 + kPanelsAtOnce; ++p) dmma884(S[p], n1[kb], xs[p][kb]);
+          }
 #pragma unroll
-        for (int p = 0; p < 4; ++p) {
-          dmma884(c_first[p], n2[1], b[p][3]);
-          dmma884(c_second[p], n3[1], b[p][1]);
-        }
+          for (int p = p0; p < p0 + kPanelsAtOnce; ++p) {
+            dmma884(c_first[p], n2[0], b[p][2], S[p]);
+            dmma884(c_second[p], n3[0], b[p][0], S[p]);
+          }
 #pragma unroll
-        for (int p = 0; p < 4; ++p) {
-          c_second[p][0] = flip_sign(c_second[p][0], sq);
-          c_second[p][1] = flip_sign(c_second[p][1], sq);
-        }
-        // mma.sync is warp-synchronous: every lane's loads of a panel are complete before any lane stores into it
+          for (int p = p0; p < p0 + kPanelsAtOnce; ++p) {
+            dmma884(c_first[p], n2[1], b[p][3]);
+            dmma884(c_second[p], n3[1], b[p][1]);
+          }
+          // mma.sync is warp-synchronous: every lane's loads of a panel are complete before any lane stores into it
 #pragma unroll
-        for (int p = 0; p < 4; ++p) {
-          const uint32_t a0 = st0 ^ ((p & 1) ? x_p0 : 0u) ^ ((p & 2) ? x_p1 : 0u);
-          sts_f64(a0, c_first[p][0]);
-          sts_f64(a0 ^ x_i0, c_first[p][1]);
-          sts_f64(a0 ^ 8u, c_second[p][0]);
-          sts_f64(a0 ^ x_i0 ^ 8u, c_second[p][1]);
+          for (int p = p0; p < p0 + kPanelsAtOnce; ++p) {
+            const uint32_t a0 = st0 ^ ((p & 1) ? x_p0 : 0u) ^ ((p & 2) ? x_p1 : 0u);
+            sts_f64(a0, c_first[p][0]);
+            sts_f64(a0 ^ x_i0, c_first[p][1]);
+            sts_f64(a0 ^ 8u, flip_sign(c_second[p][0], sq));
+            sts_f64(a0 ^ x_i0 ^ 8u, flip_sign(c_second[p][1], sq));
+          }
         }
         if (r + 1 == A.n_rounds) fence_proxy_async();
+        const long long b0 = PROF_T();
         if (chain_next && r + 1 < A.n_rounds) __syncwarp();
         else group_bar(group);
+        c_bar += PROF_T() - b0;
       }
     }
+    c_rounds += PROF_T() - w1;
     if (A.n_rounds == 0) {
       fence_proxy_async();
       group_bar(group);
     }
     if (gwarp == 0 && lane == 0) mbar_arrive(&done[s]);
   }
+  PROF_ADD(0, PROF_T() - c_t0);
+  PROF_ADD(1, c_full);
+  PROF_ADD(2, c_rounds);
+  PROF_ADD(3, c_bar);
+  PROF_ADD(7, 1);
 }
 
 }  // namespace qcsim

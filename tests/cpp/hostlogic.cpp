@@ -359,3 +359,25 @@ void hl_pipe_round_dump(const qcsim_gate* gates, int count, int n_local) {
   }
 }
 }
+
+// ---- lazy flush for a diagonal single-qubit observable (planner.h: split_queue_for_diagonal_observable) -------
+extern "C" {
+// needed[i] = 1 when gate i has to run before the observable on the qubits of qmask is read
+void hl_split_for_observable(const qcsim_gate* gates, int count, unsigned long long qmask, int* needed) {
+  std::vector<Op> ops;
+  for (int i = 0; i < count; ++i) {
+    ops.push_back(classify(gates[i].nq, gates[i].m, gates[i].flags, gates[i].q, gates[i].c1, gates[i].c2));
+    ops.back().m[63] = cplx((double)i, 0.0);  // tag (the split copies ops; entry 63 is unused below 3 qubits ... restored by index)
+  }
+  // the split keeps order, so a two-pointer walk recovers the indices
+  std::vector<Op> need, rest;
+  split_queue_for_diagonal_observable(ops, qmask, &need, &rest);
+  size_t a = 0, b = 0;
+  for (int i = 0; i < count; ++i) {
+    const bool in_need = a < need.size() && need[a].m[63] == cplx((double)i, 0.0);
+    needed[i] = in_need ? 1 : 0;
+    if (in_need) ++a;
+    else ++b;
+  }
+}
+}

@@ -323,6 +323,25 @@ def test_fused_random_circuit_vs_oracle(n, layers, mode):
             assert st["state_passes"] < len(circ) / 2, st  # really fused
 
 
+@pytest.mark.parametrize("n", [9, 14, 18])
+def test_qubit_probability_between_fused_gates_keeps_the_rest_queued(n):
+    """GetQubitProbability(q) in fusion mode runs only the queued gates that can change P(q) (engine.cu:
+    engine_flush_for_diagonal_observable); every value along the way and the final state are the reference's."""
+    circ = circuits.random_circuit(n, 6, seed=91 + n)
+    rng = np.random.default_rng(n)
+    with oracle.best_oracle(n) as ref, GpuSim(n, fusion=True) as gpu:
+        for i, (g, q, c1, c2) in enumerate(circ):
+            ref.apply(g, q, c1, c2)
+            gpu.apply(g, q, c1, c2)
+            if i % 7 == 6:
+                qq = int(rng.integers(0, n))
+                assert abs(gpu.reg.GetQubitProbability(qq) - ref.qubit_probability(qq)) <= TOL, (i, qq)
+        passes_so_far = gpu.reg.stats()["state_passes"]
+        assert maxdiff(gpu.state(), ref.state()) <= TOL
+        if n >= 14:
+            assert passes_so_far < len(circ) / 2, passes_so_far  # the probability reads did not force gate-by-gate passes
+
+
 @pytest.mark.parametrize("n", [7, 12, 14])
 def test_fused_all_gate_kinds(n):
     """every gate class (flagged and flag-less) through the tile engine, on rotating qubits, twice

@@ -562,3 +562,44 @@ def test_pipe_kernel_data_path_emulated(hl, seed, n, tile_bits, layout_search):
 def test_some_emulated_rounds_were_chained():
     """runs after test_pipe_kernel_data_path_emulated: the chained (warp-local, barrier-free) round hand-over was exercised"""
     assert _CHAINED and sum(_CHAINED) >= 1, _CHAINED
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5])
+def test_lazy_flush_for_a_qubit_probability(hl, seed):
+    """GetQubitProbability(q) only needs the queued gates that act non-diagonally on q and what those depend on
+    (planner.h: split_queue_for_diagonal_observable): running the needed gates first and the rest later is the same
+    circuit, and P(q) after the needed gates alone is already the final P(q)."""
+    n = 7
+    rng = np.random.default_rng(seed)
+    samples = [g for g in gates.all_gate_samples() if g.nq <= 2] + [g for g in gates.all_gate_samples() if g.nq == 3][:4]
+    circ = []
+    for _ in range(40):
+        g = samples[int(rng.integers(0, len(samples)))]
+        qs = [int(x) for x in rng.permutation(n)[:3]]
+        gg = g if rng.integers(0, 2) else gates.AppliedGate(g.matrix)
+        circ.append((gg, qs[0], qs[1] if g.nq > 1 else 0, qs[2] if g.nq > 2 else 0))
+    arr = pack(circ)
+    psi0 = random_state(n, seed)
+    full = psi0.copy()
+    for g, q, c1, c2 in circ:
+        full = full_matrix_apply(full, g, [q, c1, c2], n)
+    kept_any = False
+    for q in range(n):
+        needed = (C.c_int * len(circ))()
+        hl.hl_split_for_observable(arr, len(circ), C.c_ulonglong(1 << q), needed)
+        need = [i for i in range(len(circ)) if needed[i]]
+        rest = [i for i in range(len(circ)) if not needed[i]]
+        kept_any = kept_any or len(rest) > 0
+        part = psi0.copy()
+        for i in need:
+            g, a, c1, c2 = circ[i]
+            part = full_matrix_apply(part, g, [a, c1, c2], n)
+        idx = np.arange(1 << n)
+        p_part = float(np.sum(np.abs(part[(idx >> q) & 1 == 1]) ** 2))
+        p_full = float(np.sum(np.abs(full[(idx >> q) & 1 == 1]) ** 2))
+        assert abs(p_part - p_full) < 1e-12, (q, p_part, p_full)
+        for i in rest:
+            g, a, c1, c2 = circ[i]
+            part = full_matrix_apply(part, g, [a, c1, c2], n)
+        assert np.max(np.abs(part - full)) < 1e-12, q
+    assert kept_any
