@@ -493,7 +493,7 @@ int engine_flush_for_diagonal_observable(qcsim_sv* h, uint64_t qmask) {
     return e ? std::atoi(e) : 1;
   }();
   if (h->queue.empty()) return QCSIM_OK;
-  if (!lazy) return engine_flush(h);
+  if (!lazy || fusion_holds_qft(h->queue)) return engine_flush(h);  // a transform is recognised from its whole gate stream
   std::vector<Op> needed, rest;
   split_queue_for_diagonal_observable(h->queue, qmask, &needed, &rest);
   if (rest.size() < 4) return engine_flush(h);  // nothing worth keeping

@@ -257,6 +257,19 @@ static int execute_plain(qcsim_sv* h, const std::vector<Op>& ops) {
 
 int fusion_execute(qcsim_sv* h, const std::vector<Op>& ops_in) { return fusion_execute_partial(h, ops_in, nullptr); }
 
+// true when the list holds a QFT / IQFT gate stream (or the start of one): such a list must be flushed whole, a
+// subset of it would no longer be recognised and would run gate by gate
+bool fusion_holds_qft(const std::vector<Op>& ops) {
+  if (ops.size() < 10) return false;
+  for (size_t i = 0; i < ops.size(); ++i) {
+    if (!(ops[i].n_ctrl == 0 && ops[i].kind == OP_PAIR)) continue;
+    bool ran_off = false;
+    const QftMatch m = match_qft(ops, i, 4, &ran_off);
+    if (m.length > 0 || ran_off) return true;
+  }
+  return false;
+}
+
 // `deferred` != nullptr: a trailing run of ops that is still a valid QFT prefix when the list ends is
 // handed back instead of executed (the caller keeps it queued until the rest of the transform arrives).
 int fusion_execute_partial(qcsim_sv* h, const std::vector<Op>& ops_in, std::vector<Op>* deferred) {

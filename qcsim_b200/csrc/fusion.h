@@ -12,6 +12,7 @@ namespace qcsim {
 // shared-memory tile are applied in a single pass over HBM (tile_kernels.cuh) and everything else
 // runs as single-gate kernels.  Result is identical (to rounding) to applying the ops one by one.
 int fusion_execute(qcsim_sv* h, const std::vector<Op>& ops);
+bool fusion_holds_qft(const std::vector<Op>& ops);  // the list contains a QFT / IQFT gate stream or the start of one
 // same; a trailing run of ops that is still a valid QFT prefix is returned in `deferred` instead of
 // being executed (used when the bounded gate queue is flushed while a transform is still arriving)
 int fusion_execute_partial(qcsim_sv* h, const std::vector<Op>& ops, std::vector<Op>* deferred);

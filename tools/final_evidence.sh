@@ -14,7 +14,9 @@ M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_fp6
 timeout 400 ncu --metrics $M --clock-control none -c 400 --csv --log-file $O/${R}_launches_random.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-kernel-sweep > /dev/null 2>&1
 timeout 400 ncu --metrics $M --clock-control none -c 400 --csv --log-file $O/${R}_launches_qft.csv python bench.py --steps 2 --warmup 1 --workload qft --no-cpu-baseline --no-kernel-sweep > /dev/null 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_tile_pipe -s 6 -c 1 -o $O/${R}_k_tile_pipe_30q python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-kernel-sweep > /dev/null 2>&1
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_qft_pipe -s 4 -c 1 -o $O/${R}_k_qft_pipe_30q python bench.py --steps 2 --warmup 3 --workload qft --no-cpu-baseline --no-kernel-sweep > /dev/null 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_qft_pipe$ -s 4 -c 1 -o $O/${R}_k_qft_pipe_30q python bench.py --steps 2 --warmup 3 --workload qft --no-cpu-baseline --no-kernel-sweep > /dev/null 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_bit_reverse -s 1 -c 1 -o $O/${R}_k_bit_reverse_30q python bench.py --steps 2 --warmup 3 --workload qft --no-cpu-baseline --no-kernel-sweep > /dev/null 2>&1
 ls -la $O/*.ncu-rep | tail -4
 ( timeout 600 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "fused_random_circuit_vs_oracle and 13 or fused_qft_vs_oracle and 12" 2>&1 | tail -6 ) > $O/${R}_sanitizer.log; tail -4 $O/${R}_sanitizer.log
+# per-launch times of k_tile_pipe by round count (serialised launches; diagnostics)
+QCSIM_DEBUG_PLAN=3 timeout 200 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-kernel-sweep 2>&1 | grep "pipe launch" > $O/${R}_launch_times.log; wc -l $O/${R}_launch_times.log

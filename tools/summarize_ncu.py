@@ -5,7 +5,7 @@ def launch_list(path):
     hdr=rows[0]; ik=hdr.index("Kernel Name"); im=hdr.index("Metric Name"); iv=hdr.index("Metric Value"); iid=hdr.index("ID")
     d=collections.OrderedDict()
     for r in rows[1:]:
-        d.setdefault((int(r[iid]), r[ik].split("(")[0]),{})[r[im]]=float(r[iv].replace(",",""))
+        d.setdefault((int(r[iid]), r[ik].split("(")[0].split("::")[-1]),{})[r[im]]=float(r[iv].replace(",",""))
     return d
 def table(d):
     agg=collections.OrderedDict()
