@@ -43,7 +43,7 @@ for q in (30, 33):
     o = line(f"r01_bench_qft_{q}q.json")
     if d:
         rows.append((f"QFT, {q} q, 1 GPU" + (" (BASELINE config 3)" if q == 33 else ""), f"{d['ms_per_step']:.1f} ms / transform", f"{fmt(d['value'])} gate-apps/s",
-                     f"round 1: {o['ms_per_step']:.1f} ms; floor = 4 passes = {4 * 32 * 2 ** q / 6453.7e9 * 1e3:.1f} ms"))
+                     f"round 1: {o['ms_per_step']:.1f} ms; 4 TMA-staged passes + 1 reversal pass = {5 * 32 * 2 ** q / 6453.7e9 * 1e3:.1f} ms at the HBM peak"))
 for n in (2, 4, 8):
     d = line(f"r02_bench{n}_random.json")
     if d and one:
