@@ -481,7 +481,9 @@ static __global__ void __launch_bounds__(kPipeThreads, 1) k_tile_pipe(const __gr
             dmma884(c_first[p], n2[1], b[p][3]);
             dmma884(c_second[p], n3[1], b[p][1]);
           }
-          // mma.sync is warp-synchronous: every lane's loads of a panel are complete before any lane stores into it
+          // A lane stores into slots other lanes of the warp loaded from: the loads are complete (their values fed the
+          // warp-wide mma.sync above); the explicit warp barrier states that ordering for the memory model / racecheck
+          __syncwarp();
 #pragma unroll
           for (int p = p0; p < p0 + kPanelsAtOnce; ++p) {
             const uint32_t a0 = st0 ^ ((p & 1) ? x_p0 : 0u) ^ ((p & 2) ? x_p1 : 0u);
