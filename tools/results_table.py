@@ -22,7 +22,8 @@ def fmt(x, nd=1):
 
 rows = []
 ref = line("r02_bench_reference.json")
-one = line("r02_bench_random_30q.json")
+full = line("r02_bench_random_30q.json")           # full evidence run (kernel sweeps, cpu_baseline)
+one = line("r02_bench_random_30q_final.json") or full  # last measurement of the round (register-triple round planner), bench line only
 r01 = line("r01_bench_random_30q.json")
 if one:
     rf = one["roofline"]
@@ -31,7 +32,7 @@ if one:
                  f"{rf['passes_per_step']} HBM passes and {rf['rounds_per_step']} DMMA rounds per layer; `k_tile_pipe` at {rf['frac']:.2f} of the measured HBM peak, "
                  f"{rf['fp64']['achieved_tflops']:.1f} of {rf['fp64']['peak_tflops_fp64']} fp64 TFLOP/s"))
     rows.append(("same, end to end (host gate descriptors in, host result out, per layer)", f"{one['e2e']['ms_per_step']:.2f} ms / layer", f"{fmt(one['e2e']['value'])} gate-apps/s", "one GetQubitProbability per layer: only the queued gates that can change it are flushed, the rest keeps fusing across layers"))
-    k = one.get("kernels", {})
+    k = (full or one).get("kernels", {})
     if k:
         fr = [v["frac_of_peak"] for n, v in k.items() if "Measure" not in n and "Probability" not in n and "c=0" not in n and "SWAP" not in n]
         rows.append(("single-gate kernels, 30 q (H, RZ, CNOT, CPhase, CCX, dense 4x4 / 8x8)", f"{min(fr):.2f}–{max(fr):.2f} of HBM peak", "", "`kernels` / `kernels_33q` in the bench line; CNOT/SWAP with a qubit-0 partner 0.46 (16-byte granules)"))
