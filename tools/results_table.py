@@ -50,7 +50,7 @@ for n in (2, 4, 8):
     if d and one:
         ex = d.get("exchange", {})
         rows.append((f"random-circuit layer, {d['config']['qubits']} q, {n} GPUs (2^30 amplitudes per GPU)", f"{d['ms_per_step']:.2f} ms / layer", f"{fmt(d['value'])} gate-apps/s",
-                     f"weak-scaling efficiency {d['value'] / (n * one['value']):.2f} vs this table's 1-GPU line; exchange {fmt(ex.get('GBps_per_direction'), 0)} GB/s per direction"))
+                     f"weak-scaling efficiency {d['value'] / (n * (full or one)['value']):.2f} vs the 1-GPU run of the same build ({(full or one)['ms_per_step']:.1f} ms; measured before the last planner change); exchange {fmt(ex.get('GBps_per_direction'), 0)} GB/s per direction"))
     d = line(f"r02_bench{n}_qft30.json")
     if d:
         rows.append((f"QFT, {d['config']['qubits']} q, {n} GPUs", f"{d['ms_per_step']:.1f} ms / transform", f"{fmt(d['value'])} gate-apps/s", ""))
