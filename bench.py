@@ -248,7 +248,7 @@ def run_ours(args):
     if args.workload == "qft":
         dominant = "k_qft_pipe (TMA-staged radix-8/4/2 QFT pass) + k_bit_reverse (qubit reversal)"
     elif args.fusion:
-        dominant = "k_tile_pipe (fused gate block: TMA-staged tiles, DMMA 16x16 real rounds, mbarrier ring)"
+        dominant = "k_tile_pipe (fused gate block: TMA-staged tiles, rounds as three real 8x8 DMMA products, mbarrier ring)"
     else:
         dominant = "single-gate passes (k_pair_v2 dominant)"
     traffic = None
@@ -266,11 +266,12 @@ def run_ours(args):
         "bytes_per_step": algo_bytes // max(K, 1), "passes_per_step": st["state_passes"] / max(K, 1),
         "rounds_per_step": st.get("fused_rounds", 0) / max(K, 1),
         "nominal_peak_frac": round(achieved / 8000.0, 4),
-        "note": ("fused passes trade HBM passes for fp64 work: a round is a 16x16 real matrix product per 8 amplitudes (32 FMA per "
-                 "amplitude) on the FP64 tensor path (DMMA, 64 FMA/clk/SM); a pass of r rounds is fp64-bound beyond ~3 rounds, so "
-                 "frac < 1 here is fp64 time, not wasted HBM traffic; the unfused single-gate kernels in `kernels` are the HBM-bound ones"),
-        "fp64": {"fma_per_amp_per_round": 32, "fma_per_step": int(32 * st.get("fused_rounds", 0) / max(K, 1) * (1 << (n - log2w))),
-                 "achieved_tflops": round(2 * 32 * st.get("fused_rounds", 0) * (1 << (n - log2w)) / (ms * 1e-3) / 1e12, 2) if args.workload == "random" else None,
+        "note": ("fused passes trade HBM passes for fp64 work: a round is an 8x8 complex matrix per 8 amplitudes, executed as three "
+                 "real 8x8 products (24 FMA per amplitude) on the FP64 tensor path (DMMA, 64 FMA/clk/SM); per tile and round the "
+                 "tensor pipe, the shared-memory pipe and (at 3 rounds per pass) HBM need about the same time, so frac < 1 here is "
+                 "three balanced pipes queueing, not wasted HBM traffic; the unfused single-gate kernels in `kernels` are the HBM-bound ones"),
+        "fp64": {"fma_per_amp_per_round": 24, "fma_per_step": int(24 * st.get("fused_rounds", 0) / max(K, 1) * (1 << (n - log2w))),
+                 "achieved_tflops": round(2 * 24 * st.get("fused_rounds", 0) * (1 << (n - log2w)) / (ms * 1e-3) / 1e12, 2) if args.workload == "random" else None,
                  "peak_tflops_fp64": 37.2},
     }
 

@@ -30,7 +30,7 @@ if one:
     rows.append(("random-circuit layer, 30 q, 1 GPU (BASELINE config 2 width)", f"{one['ms_per_step']:.2f} ms / layer", f"{fmt(one['value'])} gate-apps/s",
                  f"round 1: {r01['ms_per_step']:.1f} ms; reference CPU arm {fmt(ref['value'], 2) if ref else '—'} gate-apps/s on {ref['cpu_baseline']['cores'] if ref else '?'} cores; "
                  f"{rf['passes_per_step']} HBM passes and {rf['rounds_per_step']} DMMA rounds per layer; `k_tile_pipe` at {rf['frac']:.2f} of the measured HBM peak, "
-                 f"{rf['fp64']['achieved_tflops']:.1f} of {rf['fp64']['peak_tflops_fp64']} fp64 TFLOP/s"))
+                 f"{2 * 24 * rf['rounds_per_step'] * 2 ** 30 / (one['ms_per_step'] * 1e-3) / 1e12:.1f} of {rf['fp64']['peak_tflops_fp64']} fp64 TFLOP/s executed (24 FMA per amplitude and round)"))
     rows.append(("same, end to end (host gate descriptors in, host result out, per layer)", f"{one['e2e']['ms_per_step']:.2f} ms / layer", f"{fmt(one['e2e']['value'])} gate-apps/s", "one GetQubitProbability per layer: only the queued gates that can change it are flushed, the rest keeps fusing across layers"))
     k = (full or one).get("kernels", {})
     if k:
