@@ -239,12 +239,17 @@ inline std::vector<RoundPlan> schedule_rounds(const std::vector<Op>& all, const 
     // Then every triple of the pending ops' target qubits as the register set: the greedy seeds above commit to the
     // first ops they meet, a fixed triple absorbs everything that fits it (11 % fewer rounds on the benchmark circuit).
     {
+      constexpr size_t kTripleWindow = 192;
       auto fill_fixed = [&](uint64_t R0) {
         Fill f;
         f.R = R0;
         uint64_t blocked_nd = 0, blocked_d = 0;
         for (size_t pos = 0; pos < remaining.size(); ++pos) {
           const int idx = remaining[pos];
+          if (pos >= kTripleWindow) {  // bounded look-ahead: 165 triples x the whole pass would be quadratic in deep passes
+            f.left.push_back(idx);
+            continue;
+          }
           const OpMasks m = masks_of(all[idx]);
           const bool conflict = ((m.nd | m.dg) & blocked_nd) != 0 || (m.nd & blocked_d) != 0;
           if (!conflict && (m.nd & ~R0) == 0) {
@@ -262,7 +267,7 @@ inline std::vector<RoundPlan> schedule_rounds(const std::vector<Op>& all, const 
         return f;
       };
       uint64_t cand = 0;
-      for (int idx : remaining) cand |= masks_of(all[idx]).nd;
+      for (size_t pos = 0; pos < remaining.size() && pos < kTripleWindow; ++pos) cand |= masks_of(all[remaining[pos]]).nd;
       int cq[64], nc = 0;
       for (int q = 0; q < 64; ++q)
         if ((cand >> q) & 1ULL) cq[nc++] = q;
