@@ -172,8 +172,17 @@ struct RoundPlan {
 // common.cuh (every tile bit folds onto the low three, class = bit mod 3), 1 = the 128 B TMA swizzle
 // (only slot bits 3..5 fold onto 0..2) with one item per lane, 2 = the TMA swizzle with the DMMA
 // fragment mapping of tile_pipe.cuh (register-bit order and item bits 0..2 chosen together).
+// What round formation decides, independent of the order of the tile qubits: register qubits (before padding with
+// unused tile qubits), variant qubits, ops.  schedule_rounds can hand it out / take it back, so that the same rounds are
+// placed on several shared-memory layouts (schedule_rounds_best_layout) without searching again.
+struct FormedRound {
+  uint64_t R = 0, V = 0;
+  std::vector<int> ops;
+};
+
 inline std::vector<RoundPlan> schedule_rounds(const std::vector<Op>& all, const PassPlan& plan, int max_variant_bits = 3,
-                                              int swizzle_kind = 0, int* conflict_cost = nullptr, bool always_chain = false) {
+                                              int swizzle_kind = 0, int* conflict_cost = nullptr, bool always_chain = false,
+                                              const std::vector<FormedRound>* preformed = nullptr, std::vector<FormedRound>* formed_out = nullptr) {
   int total_cost = 0;  // swizzle_kind 2: sum over rounds of (load degree + store degree); 2 per round = conflict-free
   const int k = (int)plan.tile.size();
   int local_of[64];
@@ -183,6 +192,11 @@ inline std::vector<RoundPlan> schedule_rounds(const std::vector<Op>& all, const 
   std::vector<int> remaining = plan.ops;
   std::vector<RoundPlan> rounds;
   std::vector<uint32_t> used_of, vtile_of;  // per round: register bits / in-tile variant bits (tile-local masks)
+  std::vector<FormedRound> formed;
+  if (preformed) {
+    formed = *preformed;
+    remaining.clear();
+  }
   while (!remaining.empty()) {
     // Greedy fill from a seed: the seed's targets become register bits first, then ops are taken in
     // program order.  Several seeds are tried (the first pending op, and the next few ops that
@@ -284,16 +298,27 @@ inline std::vector<RoundPlan> schedule_rounds(const std::vector<Op>& all, const 
       (void)replaced;  // best.R is the whole triple (a qubit none of the absorbed ops turns is an identity factor), best.V as counted
     }
     uint64_t R = best.R, V = best.V;
-    RoundPlan rp;
-    rp.ops = best.ops;
-    std::vector<int> left = best.left;
-    // free register slots: promote variant qubits that live in the tile (halves the matrix count
-    // for free), then pad with unused tile bits
+    // free register slots: promote variant qubits that live in the tile (halves the matrix count for free)
     for (int q = 0; q < 64 && __builtin_popcountll(R) < 3; ++q)
       if (((V >> q) & 1ULL) && local_of[q] >= 0) {
         R |= 1ULL << q;
         V &= ~(1ULL << q);
       }
+    FormedRound fr;
+    fr.R = R;
+    fr.V = V;
+    fr.ops = best.ops;
+    formed.push_back(fr);
+    std::vector<int> left = best.left;
+    remaining.swap(left);
+  }
+  if (formed_out) *formed_out = formed;
+  for (const FormedRound& fr : formed) {
+    uint64_t R = fr.R;
+    const uint64_t V = fr.V;
+    RoundPlan rp;
+    rp.ops = fr.ops;
+    // pad the register set with unused tile bits (high slots first: the low ones serve the lanes)
     for (int j = k - 1; j >= 0 && __builtin_popcountll(R) < 3; --j) R |= 1ULL << plan.tile[j];
     int nr = 0;
     uint32_t used = 0;
@@ -310,7 +335,6 @@ inline std::vector<RoundPlan> schedule_rounds(const std::vector<Op>& all, const 
       if (!((used >> lb) & 1u) && ((V >> plan.tile[lb]) & 1ULL)) vt |= 1u << lb;
     vtile_of.push_back(vt);
     rounds.push_back(rp);
-    remaining.swap(left);
   }
 
   // item-index bits.  Variant qubits inside the tile go to the warp-index part of the item index
@@ -577,11 +601,15 @@ inline std::vector<RoundPlan> schedule_rounds_best_layout(const std::vector<Op>&
   }
   std::vector<RoundPlan> best_rounds;
   int best_cost = 1 << 30;
+  std::vector<FormedRound> formed;  // the rounds are formed once (on the ascending order) and placed on every candidate layout
+  bool have_formed = false;
   auto consider = [&](const TmaTileGeom& g) {  // true: nothing can beat it
     PassPlan plan = plan_sorted;
     for (int j = 0; j < k; ++j) plan.tile[j] = g.slot_qubit[j];
     int cost = 0;
-    std::vector<RoundPlan> rounds = schedule_rounds(all, plan, max_variant_bits, 2, &cost, always_chain);
+    std::vector<RoundPlan> rounds = schedule_rounds(all, plan, max_variant_bits, 2, &cost, always_chain, have_formed ? &formed : nullptr,
+                                                    have_formed ? nullptr : &formed);
+    have_formed = true;
     if (cost < best_cost) {
       best_cost = cost;
       best_rounds.swap(rounds);
